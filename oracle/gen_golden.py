@@ -1,0 +1,240 @@
+"""TEST INFRASTRUCTURE — generates tests/golden/*.npz by running the REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):
+    python oracle/gen_golden.py
+It imports the reference's own geometry modules through ``oracle/ref_loader.py`` and
+records their outputs (and torch-CPU autograd gradients through them) on seeded inputs.
+The fixtures are committed; the tests that consume them run anywhere (the GPU box has no
+/root/reference).  Every array is produced by reference code paths cited inline; where
+the reference function cannot be imported (module header needs mmcv/mmdet registries)
+the fixture is composed from the reference's own importable pieces exactly as that
+function composes them, and says so.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+
+# KITTI 000000 calibration: rect / Trv2c from /root/reference/tests/test_utils/test_box_np_ops.py:8-15;
+# P2 from the KITTI calib file of the same frame (P2 @ rect @ Trv2c reproduces
+# expected_lidar2img of tests/test_data/test_datasets/test_kitti_dataset.py:226-230).
+RECT = np.array([[0.9999128, 0.01009263, -0.00851193, 0.],
+                 [-0.01012729, 0.9999406, -0.00403767, 0.],
+                 [0.00847068, 0.00412352, 0.9999556, 0.],
+                 [0., 0., 0., 1.]], dtype=np.float32)
+TRV2C = np.array([[0.00692796, -0.9999722, -0.00275783, -0.02457729],
+                  [-0.00116298, 0.00274984, -0.9999955, -0.06127237],
+                  [0.9999753, 0.00693114, -0.0011439, -0.3321029],
+                  [0., 0., 0., 1.]], dtype=np.float32)
+P2 = np.array([[707.0493, 0., 604.0814, 45.75831],
+               [0., 707.0493, 180.5066, -0.3454157],
+               [0., 0., 1., 0.004981016],
+               [0., 0., 0., 1.]], dtype=np.float32)
+IMG_HW = (375, 1242)
+PCD_RANGE = [0, -40, -3, 70.4, 40, 0.0]
+
+
+def kitti_like_boxes(rng, n):
+    cls = rng.integers(0, 3, n)
+    mean = np.array([[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]], np.float32)[cls]
+    dims = mean * rng.uniform(0.8, 1.2, (n, 3)).astype(np.float32)
+    xyz = np.stack([rng.uniform(2, 68, n), rng.uniform(-30, 30, n), rng.uniform(-2, -1, n)], 1)
+    yaw = rng.uniform(-2 * np.pi, 2 * np.pi, (n, 1))
+    return np.concatenate([xyz, dims, yaw], 1).astype(np.float32)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_loader.load_reference()
+    rng = np.random.default_rng(20261017)
+    g = {}
+
+    # --- corners / rotation / limit_period (lidar_box3d.py:49-89, cam_box3d.py:116-157,
+    #     depth_box3d.py:51-91, utils.py:10-25, 28-117)
+    boxes = kitti_like_boxes(rng, 64)
+    tb = torch.from_numpy(boxes)
+    g['boxes_lidar'] = boxes
+    g['corners_lidar'] = ref.LiDARInstance3DBoxes(tb).corners.numpy()
+    g['corners_depth'] = ref.DepthInstance3DBoxes(tb).corners.numpy()
+    g['corners_cam'] = ref.CameraInstance3DBoxes(tb).corners.numpy()
+    g['corners_cam_center_origin'] = ref.CameraInstance3DBoxes(
+        tb, origin=(0.5, 0.5, 0.5)).corners.numpy()
+    ang = torch.from_numpy(rng.uniform(-7, 7, 64).astype(np.float32))
+    g['lp_in'] = ang.numpy()
+    g['lp_pi'] = ref.limit_period(ang).numpy()
+    g['lp_2pi'] = ref.limit_period(ang, 0.5, np.pi * 2).numpy()
+    pts = torch.from_numpy(rng.normal(size=(64, 5, 3)).astype(np.float32))
+    g['rot_pts'] = pts.numpy()
+    g['rot_axis2'] = ref.rotation_3d_in_axis(pts, ang, axis=2).numpy()
+    g['rot_axis1'] = ref.rotation_3d_in_axis(pts, ang, axis=1).numpy()
+    g['rot_axis2_cw'] = ref.rotation_3d_in_axis(pts, ang, axis=2, clockwise=True).numpy()
+
+    # --- LIDAR -> CAM conversion (box_3d_mode.py:117-123,162-173 via lidar_box3d.py:177-195)
+    rt = torch.from_numpy(RECT @ TRV2C)
+    cam = ref.LiDARInstance3DBoxes(tb).convert_to(ref.Box3DMode.CAM, rt)
+    g['rect'], g['Trv2c'], g['P2'] = RECT, TRV2C, P2
+    g['boxes_cam'] = cam.tensor.numpy()
+
+    # --- points_cam2img (utils.py:175-214)
+    p3 = torch.from_numpy((rng.normal(size=(40, 3)) * [5, 2, 10] + [0, 0, 20]).astype(np.float32))
+    g['c2i_pts'] = p3.numpy()
+    g['c2i_uv'] = ref.points_cam2img(p3, torch.from_numpy(P2)).numpy()
+    g['c2i_uv_3x4'] = ref.points_cam2img(p3, torch.from_numpy(P2[:3])).numpy()
+
+    # --- variant B: body of convert_valid_bboxes (kitti_dataset_GGA_match.py:713-748) and the
+    #     clamp of bbox2result_kitti (:511-512), composed from the reference's own box classes
+    #     (the dataset module itself needs mmdet registries and cannot be imported).
+    lb = ref.LiDARInstance3DBoxes(tb.clone())
+    lb.limit_yaw(offset=0.5, period=np.pi * 2)                                   # :713
+    camb = lb.convert_to(ref.Box3DMode.CAM, rt)                                  # :730
+    uv = ref.points_cam2img(camb.corners, torch.from_numpy(P2))                  # :732-733
+    b2d = torch.cat([uv.min(dim=1)[0], uv.max(dim=1)[0]], dim=1)                 # :735-737
+    ishape = torch.tensor(IMG_HW, dtype=torch.float32)
+    vcam = ((b2d[:, 0] < ishape[1]) & (b2d[:, 1] < ishape[0]) & (b2d[:, 2] > 0) & (b2d[:, 3] > 0))
+    lim = torch.tensor(PCD_RANGE)
+    vp = ((lb.center > lim[:3]) & (lb.center < lim[3:])).all(-1)                 # :745-748
+    bb = b2d.numpy().copy()
+    bb[:, 2:] = np.minimum(bb[:, 2:], np.array(IMG_HW[::-1], np.float32))        # :511
+    bb[:, :2] = np.maximum(bb[:, :2], [0, 0])                                    # :512
+    g['varB_box2d_raw'] = b2d.numpy()
+    g['varB_box2d_clamped'] = bb.astype(np.float32)
+    g['varB_valid'] = (vcam & vp).numpy()
+    g['varB_valid_cam'] = vcam.numpy()
+    g['img_hw'] = np.array(IMG_HW)
+    g['pcd_range'] = np.array(PCD_RANGE, np.float32)
+
+    # the reference's own end-to-end golden for this path:
+    # tests/test_data/test_datasets/test_kitti_dataset.py:378-379 (box) -> :393 (bbox)
+    one = torch.tensor([[8.7314, -1.8559, -1.5997, 1.2000, 0.4800, 1.8900, -1.5808]])
+    l1 = ref.LiDARInstance3DBoxes(one.clone())
+    l1.limit_yaw(offset=0.5, period=np.pi * 2)
+    c1 = l1.convert_to(ref.Box3DMode.CAM, rt)
+    uv1 = ref.points_cam2img(c1.corners, torch.from_numpy(P2))
+    g['kitti_one_box2d'] = torch.cat([uv1.min(1)[0], uv1.max(1)[0]], 1).numpy()
+
+    # --- variant A: centerpoint_head_gga.py:252-275,317-338 composed from the reference's
+    #     rotation_3d_in_axis exactly as the head composes it (head module not importable).
+    l2i = (P2 @ RECT @ TRV2C).astype(np.float32)
+    l2i_obj = np.repeat(l2i[None], 64, 0)
+    l2i_obj[1::2, :3, 3] += rng.normal(size=(32, 3)).astype(np.float32) * 0.05  # per-object calib
+    tb_req = tb.clone().requires_grad_(True)
+
+    def variant_a(bx, l2):
+        dims = bx[:, 3:6]
+        cn = torch.from_numpy(np.stack(np.unravel_index(np.arange(8), [2] * 3), axis=1)).to(dims.dtype)
+        cn = cn[[0, 1, 3, 2, 4, 5, 7, 6]] - dims.new_tensor([0.5, 0.5, 0])
+        co = dims.view([-1, 1, 3]) * cn.reshape([1, 8, 3])
+        co = ref.rotation_3d_in_axis(co, bx[:, 6], axis=2)
+        co = co + bx[:, :3].view(-1, 1, 3)
+        co = torch.cat((co, torch.ones(co.shape[0], co.shape[1], 1)), dim=-1)
+        pim = torch.einsum('bij,bjk->bik', l2, co.permute(0, 2, 1))
+        depth = torch.maximum(pim[:, 2, None, :], torch.tensor([0.1]))
+        pix = (pim[:, :2, :] / depth).permute(0, 2, 1)
+        return torch.cat((pix[..., 0].min(-1)[0][:, None], pix[..., 1].min(-1)[0][:, None],
+                          pix[..., 0].max(-1)[0][:, None], pix[..., 1].max(-1)[0][:, None]), dim=-1)
+
+    pa = variant_a(tb_req, torch.from_numpy(l2i_obj))
+    g['varA_lidar2img'] = l2i_obj
+    g['varA_box2d'] = pa.detach().numpy()
+    gout = torch.from_numpy(rng.normal(size=(64, 4)).astype(np.float32))
+    pa.backward(gout)
+    g['varA_gout'] = gout.numpy()
+    g['varA_grad_boxes'] = tb_req.grad.numpy()
+
+    # --- variant C: pgd_head.py:413-427 (CAM boxes, origin (.5,.5,.5), cam2img 4x4)
+    cam_c = cam.tensor.clone()
+    cam_c[:, 1] -= cam_c[:, 4] * 0.5          # gravity-centre form, as PGD decodes it
+    cam_c.requires_grad_(True)
+    cc = ref.CameraInstance3DBoxes(cam_c, box_dim=7, origin=(0.5, 0.5, 0.5)).corners
+    uvc = ref.points_cam2img(cc, torch.from_numpy(P2))
+    pc = torch.cat([uvc.min(dim=1)[0], uvc.max(dim=1)[0]], dim=1)
+    pc.backward(gout)
+    g['varC_boxes_cam_center'] = cam_c.detach().numpy()
+    g['varC_box2d'] = pc.detach().numpy()
+    g['varC_grad_boxes'] = cam_c.grad.numpy()
+
+    # --- variant B gradient (autograd through the reference classes; unclamped box)
+    tb2 = tb.clone().requires_grad_(True)
+    cb2 = ref.LiDARInstance3DBoxes(tb2).convert_to(ref.Box3DMode.CAM, rt)
+    uv2 = ref.points_cam2img(cb2.corners, torch.from_numpy(P2))
+    pb = torch.cat([uv2.min(dim=1)[0], uv2.max(dim=1)[0]], dim=1)
+    pb.backward(gout)
+    g['varB_noyawlimit_box2d'] = pb.detach().numpy()
+    g['varB_grad_boxes'] = tb2.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, 'ref_geometry.npz'), **g)
+
+    # --- IoU family
+    h = {}
+    a = rng.uniform(0, 100, (200, 2))
+    b1 = np.concatenate([a, a + rng.uniform(1, 60, (200, 2))], 1)
+    c = a + rng.normal(size=(200, 2)) * 15
+    b2 = np.concatenate([c, c + rng.uniform(1, 60, (200, 2))], 1)
+    b2[:10] = b1[:10]                      # identical pairs
+    b2[10:20, :2] = b1[10:20, 2:] + 5      # disjoint pairs
+    b2[10:20, 2:] = b2[10:20, :2] + 7
+    b2[20:24] = b1[20:24]
+    b2[20:24, 0] = b1[20:24, 2]            # touching edges (zero-width overlap)
+    b2[20:24, 2] = b2[20:24, 0] + 3
+    h['b1'], h['b2'] = b1, b2
+    # image_box_overlap (kitti_utils/eval.py:85-114), numba, float64 and the mixed
+    # float32-dt / float64-gt typing pseudo_label_matching_kitti feeds it
+    # (tools/utils_pseudo_labels_gga.py:45 passes dt first; dt bbox is float32 from
+    #  convert_valid_bboxes' .numpy(), gt bbox float64 from the info pkl).
+    h['ibo_f64'] = ref.image_box_overlap(b1[:50], b2[:30])
+    h['ibo_f32_f64'] = ref.image_box_overlap(b1[:50].astype(np.float32), b2[:30])
+    h['ibo_f32_f32'] = ref.image_box_overlap(b1[:50].astype(np.float32), b2[:30].astype(np.float32))
+    # axis_aligned_bbox_overlaps_3d (iou3d_calculator.py:210-329) on boxes with z in [0, 1]:
+    # the z factors are exactly 1, so the values equal the 2D formula of mmdet bbox_overlaps.
+    def to3(b):
+        z0 = np.zeros((b.shape[0], 1))
+        return torch.from_numpy(np.concatenate([b[:, :2], z0, b[:, 2:], z0 + 1], 1).astype(np.float32))
+    t1, t2 = to3(b1).requires_grad_(True), to3(b2)
+    iou = ref.axis_aligned_bbox_overlaps_3d(t1, t2, mode='iou', is_aligned=True)
+    giou = ref.axis_aligned_bbox_overlaps_3d(t1, t2, mode='giou', is_aligned=True)
+    h['aa3d_iou'], h['aa3d_giou'] = iou.detach().numpy(), giou.detach().numpy()
+    w = torch.from_numpy(rng.uniform(0, 1, 200).astype(np.float32))
+    ((1 - giou) * w).sum().backward()
+    h['w'] = w.numpy()
+    h['aa3d_giou_loss_grad_b1'] = t1.grad.numpy()[:, [0, 1, 3, 4]]
+    t1b = to3(b1).requires_grad_(True)
+    iou_b = ref.axis_aligned_bbox_overlaps_3d(t1b, t2, mode='iou', is_aligned=True)
+    ((1 - iou_b) * w).sum().backward()
+    h['aa3d_iou_loss_grad_b1'] = t1b.grad.numpy()[:, [0, 1, 3, 4]]
+    # true 3D boxes for the AxisAlignedIoULoss twin
+    a3 = rng.uniform(0, 10, (64, 3))
+    q1 = np.concatenate([a3, a3 + rng.uniform(0.5, 5, (64, 3))], 1).astype(np.float32)
+    c3 = a3 + rng.normal(size=(64, 3))
+    q2 = np.concatenate([c3, c3 + rng.uniform(0.5, 5, (64, 3))], 1).astype(np.float32)
+    h['q1'], h['q2'] = q1, q2
+    h['aa3d_iou_3d'] = ref.axis_aligned_bbox_overlaps_3d(
+        torch.from_numpy(q1), torch.from_numpy(q2), mode='iou', is_aligned=True).numpy()
+    h['aa3d_giou_3d'] = ref.axis_aligned_bbox_overlaps_3d(
+        torch.from_numpy(q1), torch.from_numpy(q2), mode='giou', is_aligned=True).numpy()
+    np.savez_compressed(os.path.join(OUT, 'ref_iou.npz'), **h)
+
+    # --- numpy/numba membership twin (box_np_ops.py:353-376) — the a6 contract ("next" row)
+    m = {}
+    mb = kitti_like_boxes(rng, 16)
+    n_in = 600
+    sel = rng.integers(0, 16, n_in)
+    loc = (rng.uniform(-0.6, 0.6, (n_in, 3)) * mb[sel, 3:6]).astype(np.float32)
+    cs, sn = np.cos(mb[sel, 6]), np.sin(mb[sel, 6])
+    pin = np.stack([mb[sel, 0] + loc[:, 0] * cs - loc[:, 1] * sn,
+                    mb[sel, 1] + loc[:, 0] * sn + loc[:, 1] * cs,
+                    mb[sel, 2] + mb[sel, 5] * 0.5 + loc[:, 2]], 1).astype(np.float32)
+    pout = np.stack([rng.uniform(0, 70, 400), rng.uniform(-40, 40, 400), rng.uniform(-3, 1, 400)], 1)
+    mp = np.concatenate([pin, pout.astype(np.float32)], 0)
+    m['pts'], m['boxes'] = mp, mb
+    m['points_in_rbbox'] = ref.box_np_ops.points_in_rbbox(mp, mb)
+    np.savez_compressed(os.path.join(OUT, 'ref_rbbox.npz'), **m)
+    print('wrote', sorted(os.listdir(OUT)))
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,144 @@
+"""TEST INFRASTRUCTURE — loads the reference's own Python files read-only.
+
+Only usable where ``/root/reference`` exists (the build container).  It is used by
+``oracle/gen_golden.py`` to generate the committed fixtures under ``tests/golden/``
+and by the container-only validation tests; nothing on the GPU box imports it
+(``/root/reference`` does not exist there), and nothing in ``gga_b200/`` imports it.
+
+``import mmdet3d`` fails here (no mmcv / mmdet wheels, no network), so the geometry
+modules of the reference are loaded *by path* under their real module names, with
+namespace stubs for the packages in between and a stub ``mmcv.ops`` exposing the three
+names ``base_box3d.py:7`` imports.  The membership ops injected into that stub are
+chosen by the caller: the CPU oracle (validation here) or the CUDA op (GPU box).
+"""
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get('GGA_REFERENCE_ROOT', '/root/reference')
+
+
+def available():
+    return os.path.isfile(os.path.join(REF_ROOT, 'mmdet3d/core/bbox/structures/utils.py'))
+
+
+def _ns(name):
+    m = sys.modules.get(name)
+    if m is None:
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    return m
+
+
+def _load(name, rel):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+_CACHE = {}
+
+
+def load_reference(points_in_boxes_all=None, points_in_boxes_part=None):
+    """Returns a namespace with the reference's own geometry callables.
+
+    The two arguments become ``mmcv.ops.points_in_boxes_all/_part`` as seen by the
+    reference's box classes (``base_box3d.py:7,534,566``).
+    """
+    if not available():
+        raise RuntimeError(f'reference tree not found at {REF_ROOT}')
+    if 'ns' in _CACHE:
+        ops = sys.modules['mmcv.ops']
+        bb = sys.modules['mmdet3d.core.bbox.structures.base_box3d']
+        if points_in_boxes_all is not None:
+            ops.points_in_boxes_all = points_in_boxes_all
+            bb.points_in_boxes_all = points_in_boxes_all
+        if points_in_boxes_part is not None:
+            ops.points_in_boxes_part = points_in_boxes_part
+            bb.points_in_boxes_part = points_in_boxes_part
+        return _CACHE['ns']
+
+    for n in ['mmdet3d', 'mmdet3d.core', 'mmdet3d.core.utils', 'mmdet3d.core.bbox',
+              'mmdet3d.core.bbox.structures', 'mmdet3d.core.points', 'mmcv', 'mmcv.ops',
+              'mmdet3d.core.evaluation', 'mmdet3d.core.evaluation.kitti_utils',
+              'mmdet3d.core.bbox.iou_calculators', 'mmdet', 'mmdet.core', 'mmdet.core.bbox',
+              'mmdet.core.bbox.iou_calculators', 'mmdet.core.bbox.iou_calculators.builder']:
+        _ns(n)
+
+    def _missing(*a, **k):
+        raise RuntimeError('membership op not injected into the reference loader')
+
+    ops = sys.modules['mmcv.ops']
+    ops.box_iou_rotated = None
+    ops.points_in_boxes_all = points_in_boxes_all or _missing
+    ops.points_in_boxes_part = points_in_boxes_part or _missing
+
+    ac = _load('mmdet3d.core.utils.array_converter', 'mmdet3d/core/utils/array_converter.py')
+    sys.modules['mmdet3d.core.utils'].array_converter = ac.array_converter
+    sys.modules['mmdet3d.core.utils'].ArrayConverter = ac.ArrayConverter
+
+    S = 'mmdet3d/core/bbox/structures/'
+    u = _load('mmdet3d.core.bbox.structures.utils', S + 'utils.py')
+    st = sys.modules['mmdet3d.core.bbox.structures']
+    for k in ('limit_period', 'points_cam2img', 'rotation_3d_in_axis', 'points_img2cam',
+              'xywhr2xyxyr', 'get_box_type', 'mono_cam_box2vis', 'get_proj_mat_by_coord_type',
+              'yaw2local'):
+        setattr(st, k, getattr(u, k))
+
+    P = 'mmdet3d/core/points/'
+    bp = _load('mmdet3d.core.points.base_points', P + 'base_points.py')
+    cp = _load('mmdet3d.core.points.cam_points', P + 'cam_points.py')
+    dp = _load('mmdet3d.core.points.depth_points', P + 'depth_points.py')
+    lp = _load('mmdet3d.core.points.lidar_points', P + 'lidar_points.py')
+    pts = sys.modules['mmdet3d.core.points']
+    pts.BasePoints, pts.CameraPoints = bp.BasePoints, cp.CameraPoints
+    pts.DepthPoints, pts.LiDARPoints = dp.DepthPoints, lp.LiDARPoints
+
+    bb = _load('mmdet3d.core.bbox.structures.base_box3d', S + 'base_box3d.py')
+    lb = _load('mmdet3d.core.bbox.structures.lidar_box3d', S + 'lidar_box3d.py')
+    cb = _load('mmdet3d.core.bbox.structures.cam_box3d', S + 'cam_box3d.py')
+    db = _load('mmdet3d.core.bbox.structures.depth_box3d', S + 'depth_box3d.py')
+    bm = _load('mmdet3d.core.bbox.structures.box_3d_mode', S + 'box_3d_mode.py')
+    cm = _load('mmdet3d.core.bbox.structures.coord_3d_mode', S + 'coord_3d_mode.py')
+    for mod in (st, sys.modules['mmdet3d.core.bbox']):
+        mod.BaseInstance3DBoxes = bb.BaseInstance3DBoxes
+        mod.LiDARInstance3DBoxes = lb.LiDARInstance3DBoxes
+        mod.CameraInstance3DBoxes = cb.CameraInstance3DBoxes
+        mod.DepthInstance3DBoxes = db.DepthInstance3DBoxes
+        mod.Box3DMode = bm.Box3DMode
+        mod.Coord3DMode = cm.Coord3DMode
+        for k in ('limit_period', 'points_cam2img', 'rotation_3d_in_axis', 'get_box_type'):
+            setattr(mod, k, getattr(u, k))
+    sys.modules['mmdet3d.core.bbox'].structures = st
+
+    np_ops = _load('mmdet3d.core.bbox.box_np_ops', 'mmdet3d/core/bbox/box_np_ops.py')
+    sys.modules['mmdet3d.core.bbox'].box_np_ops = np_ops
+    ev = _load('mmdet3d.core.evaluation.kitti_utils.eval',
+               'mmdet3d/core/evaluation/kitti_utils/eval.py')
+
+    # iou3d_calculator.py:3-5 pulls two mmdet names at import time; only the in-file
+    # axis_aligned_bbox_overlaps_3d (:210-329) is used from it.
+    class _Reg:
+        def register_module(self, *a, **k):
+            return lambda c: c
+    sys.modules['mmdet.core.bbox'].bbox_overlaps = None
+    sys.modules['mmdet.core.bbox.iou_calculators.builder'].IOU_CALCULATORS = _Reg()
+    iou3d = _load('mmdet3d.core.bbox.iou_calculators.iou3d_calculator',
+                  'mmdet3d/core/bbox/iou_calculators/iou3d_calculator.py')
+
+    ns = types.SimpleNamespace(
+        utils=u, limit_period=u.limit_period, points_cam2img=u.points_cam2img,
+        rotation_3d_in_axis=u.rotation_3d_in_axis, points_img2cam=u.points_img2cam,
+        BaseInstance3DBoxes=bb.BaseInstance3DBoxes, LiDARInstance3DBoxes=lb.LiDARInstance3DBoxes,
+        CameraInstance3DBoxes=cb.CameraInstance3DBoxes, DepthInstance3DBoxes=db.DepthInstance3DBoxes,
+        Box3DMode=bm.Box3DMode, Coord3DMode=cm.Coord3DMode,
+        DepthPoints=dp.DepthPoints, LiDARPoints=lp.LiDARPoints, CameraPoints=cp.CameraPoints,
+        box_np_ops=np_ops, kitti_eval=ev, image_box_overlap=ev.image_box_overlap,
+        axis_aligned_bbox_overlaps_3d=iou3d.axis_aligned_bbox_overlaps_3d,
+        mmcv_ops=ops)
+    _CACHE['ns'] = ns
+    return ns
