@@ -1,0 +1,21 @@
+"""gga_b200 — B200 (sm_100a) implementation of GGA's geometry hot path:
+membership masking, 3D-box -> 2D-box projection, IoU/GIoU/L1 consistency loss + backward,
+pseudo-label matching.  Host side mirrors the reference's function / loss-module API; the
+compute is hand-written CUDA behind the C ABI of include/gga_b200.h.  No CPU fallback."""
+from . import _lib
+from .ops import (points_in_boxes_all, points_in_boxes_bits, points_in_boxes_cpu, points_in_boxes_part,
+                  row_words, unpack_bits)
+from .project import box3d_project, pad_proj
+from .losses import (GIoULoss, IoULoss, L1Loss, ProjectedGIoULoss, ProjectedIoULoss, ProjectedL1Loss,
+                     box2d_loss, projected_box_loss)
+from .matching import convert_valid_bboxes_batch, image_box_overlap, match_dt_to_gt
+from .head import boundary_projection_loss, get_prediction_single, gga_calculate_rotation
+
+__all__ = [
+    'points_in_boxes_all', 'points_in_boxes_part', 'points_in_boxes_cpu', 'points_in_boxes_bits',
+    'row_words', 'unpack_bits', 'box3d_project', 'pad_proj', 'box2d_loss', 'projected_box_loss',
+    'ProjectedGIoULoss', 'ProjectedIoULoss', 'ProjectedL1Loss', 'GIoULoss', 'IoULoss', 'L1Loss',
+    'convert_valid_bboxes_batch', 'image_box_overlap', 'match_dt_to_gt', 'get_prediction_single',
+    'gga_calculate_rotation', 'boundary_projection_loss',
+]
+__version__ = '0.1.0'

@@ -1,0 +1,176 @@
+"""Synthetic KITTI / SUN-RGBD shaped frames for tests and bench.
+
+fp32, ``numpy.random.default_rng(1000 * cfg + frame)``.  Pure data generation (numpy on the
+host); nothing here is on the measured path.
+"""
+import numpy as np
+
+# KITTI 000000 calibration (rect / Trv2c: /root/reference/tests/test_utils/test_box_np_ops.py:8-15;
+# P2 of the same frame; P2 @ rect @ Trv2c reproduces expected_lidar2img of
+# /root/reference/tests/test_data/test_datasets/test_kitti_dataset.py:226-230).
+KITTI_RECT = np.array([[0.9999128, 0.01009263, -0.00851193, 0.], [-0.01012729, 0.9999406, -0.00403767, 0.],
+                       [0.00847068, 0.00412352, 0.9999556, 0.], [0., 0., 0., 1.]], dtype=np.float32)
+KITTI_TRV2C = np.array([[0.00692796, -0.9999722, -0.00275783, -0.02457729],
+                        [-0.00116298, 0.00274984, -0.9999955, -0.06127237],
+                        [0.9999753, 0.00693114, -0.0011439, -0.3321029], [0., 0., 0., 1.]], dtype=np.float32)
+KITTI_P2 = np.array([[707.0493, 0., 604.0814, 45.75831], [0., 707.0493, 180.5066, -0.3454157],
+                     [0., 0., 1., 0.004981016], [0., 0., 0., 1.]], dtype=np.float32)
+KITTI_IMG_HW = (375, 1242)
+KITTI_PCD_RANGE = (0.0, -40.0, -3.0, 70.4, 40.0, 1.0)   # gga_kitti_config.py:2
+KITTI_MATCH_RANGE = (0.0, -40.0, -3.0, 70.4, 40.0, 0.0)  # pcd_limit_range of the KITTI datasets
+
+CLASS_DIMS = np.array([[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]], dtype=np.float32)
+
+# the named configurations of BASELINE.json (cfg id -> shape)
+CONFIGS = {
+    1: dict(name='kitti_single_frame_cpu', N=120000, M=64, G=8, frames_per_gpu=1, kind='kitti'),
+    2: dict(name='gga_kitti_train', N=120000, M=256, G=8, frames_per_gpu=8, kind='kitti'),
+    3: dict(name='fcaf3d_sunrgbd', N=50000, M=512, G=8, frames_per_gpu=8, kind='sunrgbd'),
+    4: dict(name='pseudo_label_matching', N=0, M=512, G=8, frames_per_gpu=464, kind='kitti'),
+    5: dict(name='roofline_stress', N=2000000, M=1024, G=8, frames_per_gpu=1, kind='kitti'),
+}
+
+
+def kitti_lidar2img():
+    return (KITTI_P2 @ KITTI_RECT @ KITTI_TRV2C).astype(np.float32)
+
+
+def sunrgbd_depth2img():
+    K = np.array([[529.5, 0, 365.0], [0, 529.5, 265.0], [0, 0, 1]], dtype=np.float32)
+    t = np.deg2rad(6.0)
+    # depth (x right, y forward, z up) -> camera (x right, y down, z forward), tilted about x
+    Rt = np.array([[1, 0, 0], [0, -np.sin(t), -np.cos(t)], [0, np.cos(t), -np.sin(t)]], dtype=np.float32)
+    m = np.eye(4, dtype=np.float32)
+    m[:3, :3] = K @ Rt
+    return m
+
+
+def make_boxes(rng, M, kind='kitti'):
+    if kind == 'sunrgbd':
+        xyz = np.stack([rng.uniform(-4, 4, M), rng.uniform(1, 7, M), rng.uniform(-1.5, 0.5, M)], 1)
+        dims = rng.uniform(0.3, 2.5, (M, 3))
+    else:
+        xyz = np.stack([rng.uniform(1, 69.4, M), rng.uniform(-39, 39, M), rng.uniform(-2, -1, M)], 1)
+        dims = CLASS_DIMS[rng.integers(0, 3, M)] * rng.uniform(0.8, 1.2, (M, 3))
+    yaw = rng.uniform(-np.pi, np.pi, (M, 1))
+    boxes = np.concatenate([xyz, dims, yaw], 1).astype(np.float32)
+    # a few axis-aligned boxes with exactly representable faces carry the adversarial points
+    k = min(4, M)
+    boxes[:k, 6] = 0.0
+    boxes[:k, 3:6] = np.float32([4.0, 2.0, 1.5])
+    boxes[:k, :3] = np.round(boxes[:k, :3] * 4) / 4
+    return boxes
+
+
+def make_points(rng, N, boxes, kind='kitti', sort_azimuth=True):
+    """[N, 4] (x, y, z, r): 80 % uniform in range, 20 % inside 1.2x enlarged boxes, plus up to
+    64 adversarial points exactly on faces / edges of the yaw-0 boxes."""
+    M = boxes.shape[0]
+    n_adv = min(64, N // 8) if M >= 1 else 0
+    n_in = int(0.2 * N) if M >= 1 else 0
+    n_bg = N - n_in - n_adv
+    if kind == 'sunrgbd':
+        bg = np.stack([rng.uniform(-5, 5, n_bg), rng.uniform(0, 8, n_bg), rng.uniform(-2, 1, n_bg)], 1)
+    else:
+        bg = np.stack([rng.uniform(0, 70.4, n_bg), rng.uniform(-40, 40, n_bg), rng.uniform(-3, 1, n_bg)], 1)
+    parts = [bg]
+    if n_in:
+        sel = rng.integers(0, M, n_in)
+        loc = rng.uniform(-0.6, 0.6, (n_in, 3)) * boxes[sel, 3:6]
+        c, s = np.cos(boxes[sel, 6]), np.sin(boxes[sel, 6])
+        parts.append(np.stack([boxes[sel, 0] + loc[:, 0] * c - loc[:, 1] * s,
+                               boxes[sel, 1] + loc[:, 0] * s + loc[:, 1] * c,
+                               boxes[sel, 2] + boxes[sel, 5] * 0.5 + loc[:, 2]], 1))
+    if n_adv:
+        k = min(4, M)
+        adv = []
+        for j in range(n_adv):
+            b = boxes[j % k]
+            hx, hy, dz = b[3] / 2, b[4] / 2, b[5]
+            case = (j // k) % 8
+            off = [(hx, 0, dz / 2), (-hx, 0, dz / 2), (0, hy, dz / 2), (0, -hy, dz / 2),   # open x/y faces
+                   (0, 0, 0), (0, 0, dz),                                                  # closed z faces
+                   (hx, hy, dz), (hx * 0.5, hy * 0.5, dz * 0.5)][case]
+            adv.append([b[0] + off[0], b[1] + off[1], b[2] + off[2]])
+        parts.append(np.asarray(adv))
+    xyz = np.concatenate(parts, 0).astype(np.float32)
+    pts = np.concatenate([xyz, rng.uniform(0, 1, (N, 1)).astype(np.float32)], 1)
+    if sort_azimuth:
+        pts = pts[np.argsort(np.arctan2(pts[:, 1], pts[:, 0]), kind='stable')]
+    else:
+        pts = pts[rng.permutation(N)]
+    return np.ascontiguousarray(pts, dtype=np.float32)
+
+
+def _project_kitti_cam_np(boxes):
+    """numpy restatement of variant B (target generation only)."""
+    b = boxes.astype(np.float32).copy()
+    two_pi = np.float32(2 * np.pi)
+    b[:, 6] = b[:, 6] - np.floor(b[:, 6] / two_pi + np.float32(0.5)) * two_pi
+    rt = KITTI_RECT @ KITTI_TRV2C
+    xyz = np.concatenate([b[:, :3], np.ones((len(b), 1), np.float32)], 1) @ rt.T
+    dims = b[:, [3, 5, 4]]
+    yaw = -b[:, 6] - np.float32(np.pi / 2)
+    yaw = yaw - np.floor(yaw / two_pi + np.float32(0.5)) * two_pi
+    bits = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 1], [0, 1, 0], [1, 0, 0], [1, 0, 1], [1, 1, 1], [1, 1, 0]],
+                    np.float32) - np.float32([0.5, 1.0, 0.5])
+    loc = dims[:, None, :] * bits[None]
+    c, s = np.cos(yaw)[:, None], np.sin(yaw)[:, None]
+    cor = np.stack([loc[..., 0] * c + loc[..., 2] * s, loc[..., 1], -loc[..., 0] * s + loc[..., 2] * c], -1)
+    cor = cor + xyz[:, None, :3]
+    q = np.concatenate([cor, np.ones(cor.shape[:2] + (1,), np.float32)], -1) @ KITTI_P2.T
+    uv = q[..., :2] / q[..., 2:3]
+    return np.concatenate([uv.min(1), uv.max(1)], 1).astype(np.float32)
+
+
+def make_targets(rng, boxes, G, img_hw=KITTI_IMG_HW):
+    """[G, 4] 2D boxes: variant-B projection of a jittered copy of G boxes, clamped."""
+    G = min(G, boxes.shape[0])
+    jb = boxes[:G].copy()
+    jb[:, :3] += rng.normal(0, 0.2, (G, 3)).astype(np.float32)
+    jb[:, 6] += rng.normal(0, 0.1, G).astype(np.float32)
+    t = _project_kitti_cam_np(jb)
+    H, W = img_hw
+    t[:, 0] = np.clip(t[:, 0], 0, W - 2); t[:, 1] = np.clip(t[:, 1], 0, H - 2)
+    t[:, 2] = np.clip(t[:, 2], t[:, 0] + 1, W); t[:, 3] = np.clip(t[:, 3], t[:, 1] + 1, H)
+    return t.astype(np.float32)
+
+
+def make_frame(cfg, frame, N=None, M=None, G=None, sort_azimuth=True):
+    """One synthetic frame of configuration `cfg` (1..5)."""
+    c = CONFIGS[cfg]
+    N = c['N'] if N is None else N
+    M = c['M'] if M is None else M
+    G = c['G'] if G is None else G
+    kind = c['kind']
+    rng = np.random.default_rng(1000 * cfg + frame)
+    boxes = make_boxes(rng, M, kind)
+    pts = make_points(rng, N, boxes, kind, sort_azimuth) if N else np.zeros((0, 4), np.float32)
+    if kind == 'sunrgbd':
+        l2i = sunrgbd_depth2img()
+        hw = (530, 730)
+        tg = np.stack([rng.uniform(0, 600, G), rng.uniform(0, 400, G)], 1)
+        tg = np.concatenate([tg, tg + rng.uniform(20, 200, (G, 2))], 1).astype(np.float32)
+    else:
+        l2i = kitti_lidar2img()
+        hw = KITTI_IMG_HW
+        tg = make_targets(rng, boxes, G)
+    target = tg[np.arange(M) % len(tg)] if len(tg) else np.zeros((M, 4), np.float32)
+    return dict(points=pts, boxes=boxes, lidar2img=l2i, img_hw=hw, gt2d=tg,
+                target=np.ascontiguousarray(target, dtype=np.float32),
+                weight=np.ones((M,), np.float32))
+
+
+def make_batch(cfg, frame0, n_frames, **kw):
+    """Stacks `n_frames` frames: points [F, N, 4], boxes [F, M, 7], lidar2img [F, M, 4, 4]
+    (one calib per object, the GGA_lidar2img layout), target [F, M, 4], weight [F, M]."""
+    fr = [make_frame(cfg, frame0 + i, **kw) for i in range(n_frames)]
+    M = fr[0]['boxes'].shape[0]
+    return dict(
+        points=np.stack([f['points'] for f in fr]),
+        boxes=np.stack([f['boxes'] for f in fr]),
+        lidar2img=np.stack([np.repeat(f['lidar2img'][None], M, 0) for f in fr]),
+        target=np.stack([f['target'] for f in fr]),
+        weight=np.stack([f['weight'] for f in fr]),
+        gt2d=[f['gt2d'] for f in fr],
+        img_hw=fr[0]['img_hw'])

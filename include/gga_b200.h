@@ -1,0 +1,187 @@
+/*
+ * gga_b200.h — C ABI of libgga_b200.so: the B200 (sm_100a) implementation of GGA's
+ * geometry hot path.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions (mirroring how the reference's ops are called):
+ *   - every `const float*` / output pointer is a DEVICE pointer unless the function name
+ *     ends in `_host`; the caller owns all buffers; inputs are never written;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream) and the call returns without synchronising, like the mmcv ops run on the
+ *     current torch stream (mmcv/ops/points_in_boxes.py; call sites
+ *     /root/reference/mmdet3d/core/bbox/structures/base_box3d.py:534,566);
+ *   - return value 0 = OK, negative = error (no exceptions cross the ABI; the Python
+ *     wrapper turns them into RuntimeError like mmcv's TORCH_CHECK);
+ *     gga_last_error() returns a thread-local message for the last failure;
+ *   - fp32 data, int32 indices; `num_points` = M and `num_boxes` = T in mmcv's naming.
+ */
+#ifndef GGA_B200_H_
+#define GGA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGA_OK 0
+#define GGA_ERR_INVALID (-1)     /* bad argument (shape, stride, null pointer) */
+#define GGA_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+#define GGA_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve (e.g. too many boxes) */
+
+int gga_version(void);
+const char* gga_last_error(void);
+/* sm count, compute capability and total memory of the current device */
+int gga_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ------------------------------------------------------------------------------------
+ * Part 1 — point -> 3D box membership.
+ * Replaces mmcv.ops.points_in_boxes_{all,part,cpu} as re-exported at
+ * /root/reference/mmdet3d/ops/__init__.py:12-13 and bound at
+ * /root/reference/mmdet3d/core/bbox/structures/base_box3d.py:7.
+ * Contract (bit-exact, the CPU one): SURVEY.md Appendix A.1 / oracle/pib_oracle.c.
+ *   points : [B, num_points, pts_stride] floats, xyz first (pts_stride 3 = mmcv layout,
+ *            4 = (x,y,z,r) KITTI layout, any >= 3 accepted)
+ *   boxes  : [B, num_boxes, 7] = (x, y, z_bottom, dx, dy, dz, rz)
+ * ---------------------------------------------------------------------------------- */
+
+/* Words per point row of the bit-packed mask for `num_boxes` boxes:
+ * 1, 2 or 4 for <= 32 / 64 / 128 boxes, else 8 * ceil(num_boxes / 256).
+ * Box t of a point is bit (t & 31) of word (t >> 5); padding bits are zero. */
+int gga_pib_row_words(int num_boxes);
+
+/* bits : uint32 [B, num_points, gga_pib_row_words(num_boxes)] */
+int gga_points_in_boxes_bits(const float* points, int pts_stride, const float* boxes,
+                             uint32_t* bits, int B, int num_points, int num_boxes, void* stream);
+
+/* out : int32 [B, num_points, num_boxes], 0/1 — exact layout of mmcv points_in_boxes_all.
+ * Every element is written (no pre-zeroing needed). */
+int gga_points_in_boxes_all(const float* points, int pts_stride, const float* boxes, int32_t* out,
+                            int B, int num_points, int num_boxes, void* stream);
+
+/* out : int32 [B, num_points], index of the first enclosing box or -1 — mmcv
+ * points_in_boxes_part. */
+int gga_points_in_boxes_part(const float* points, int pts_stride, const float* boxes,
+                             int32_t* out, int B, int num_points, int num_boxes, void* stream);
+
+/* HOST buffers in and out (the points_in_boxes_cpu signature: CPU tensors), computed on
+ * the current device: H2D, kernel, D2H, synchronous.  out : int32 [B, num_points, num_boxes]. */
+int gga_points_in_boxes_all_host(const float* points, int pts_stride, const float* boxes,
+                                 int32_t* out, int B, int num_points, int num_boxes);
+
+/* Tuning knobs (0 = automatic): BEV cull-grid cells per side, CTAs per frame. */
+int gga_pib_set_tuning(int grid_cells, int ctas_per_frame);
+
+/* ------------------------------------------------------------------------------------
+ * Part 2 + 3 — box corners -> projection -> 8-corner min/max -> (clamped) 2D box, and the
+ * projected-box vs 2D-target loss with its backward pass, one launch for n boxes.
+ *
+ * mode (which reference function is mirrored):
+ *   GGA_PROJ_LIDAR_DIRECT : CenterHead_GGA.get_prediction_single,
+ *        /root/reference/mmdet3d/models/dense_heads/centerpoint_head_gga.py:252-275,317-338.
+ *        boxes = LiDAR (x,y,z_bottom,dx,dy,dz,yaw); proj = lidar2img 4x4; depth = max(q.z, depth_clamp).
+ *   GGA_PROJ_KITTI_CAM    : KittiDataset_GGA*.convert_valid_bboxes,
+ *        /root/reference/mmdet3d/datasets/kitti_dataset_GGA_match.py:713-748 (+ clamp :511-512).
+ *        boxes = LiDAR; rt = rect @ Trv2c 4x4; proj = P2 padded to 4x4; no depth clamp.
+ *   GGA_PROJ_CAM_CENTER   : PGDHead.get_proj_bbox2d core,
+ *        /root/reference/mmdet3d/models/dense_heads/pgd_head.py:413-427.
+ *        boxes = CAM (x,y,z,l,h,w,yaw) with origin (0.5,0.5,0.5); proj = cam2img 4x4.
+ *   GGA_PROJ_CAM_BOTTOM   : CameraInstance3DBoxes.corners + points_cam2img
+ *        (cam_box3d.py:116-157, utils.py:175-214); boxes = CAM, origin (0.5,1.0,0.5).
+ * loss kind:
+ *   GGA_LOSS_NONE, GGA_LOSS_GIOU (mmdet GIoULoss: 1 - giou, eps),
+ *   GGA_LOSS_IOU_LINEAR / _SQUARE / _LOG (mmdet IoULoss modes), GGA_LOSS_L1 (mmdet L1Loss,
+ *   the GGA Boundary-Projection Loss, centerpoint_head_gga.py:714-720).
+ * ---------------------------------------------------------------------------------- */
+#define GGA_PROJ_LIDAR_DIRECT 0
+#define GGA_PROJ_KITTI_CAM 1
+#define GGA_PROJ_CAM_CENTER 2
+#define GGA_PROJ_CAM_BOTTOM 3
+
+#define GGA_LOSS_NONE 0
+#define GGA_LOSS_GIOU 1
+#define GGA_LOSS_IOU_LINEAR 2
+#define GGA_LOSS_IOU_SQUARE 3
+#define GGA_LOSS_IOU_LOG 4
+#define GGA_LOSS_L1 5
+
+typedef struct gga_box_loss_args {
+  /* inputs */
+  const float* boxes;      /* [n, 7] */
+  const float* proj;       /* 4x4 row-major; element stride between boxes = proj_stride floats */
+  int proj_stride;         /* 16 = one matrix per box (GGA_lidar2img), 0 = one shared matrix;
+                              with frame_of_box: matrix index = frame */
+  const float* rt;         /* KITTI_CAM only: rect @ Trv2c 4x4, same striding rule as proj */
+  int rt_stride;
+  const int32_t* frame_of_box; /* optional [n]: selects proj/rt matrix (and img_hw) per frame */
+  const float* img_hw;     /* optional [F or 1, 2] = (H, W): clamp + validity (KITTI_CAM) */
+  const float* pcd_range;  /* optional [6]: centre-in-range validity (KITTI_CAM) */
+  const float* target;     /* [n, 4] 2D boxes (x1,y1,x2,y2); required unless loss NONE */
+  const float* weight;     /* optional; [n] (weight_cols 1) or [n, 4] (weight_cols 4) */
+  int weight_cols;
+  const float* grad_loss;  /* optional [n]: upstream gradient per box (reduction 'none');
+                              NULL = every box gets grad_scale */
+  int n;
+  int mode;                /* GGA_PROJ_* */
+  int loss_kind;           /* GGA_LOSS_* */
+  int clamp_to_image;      /* 1: box2d output clamped to [0,W]x[0,H] (gradient is that of the raw box) */
+  float depth_clamp;       /* LIDAR_DIRECT: 0.1 in the reference; <= 0 disables */
+  float eps;               /* IoU/GIoU eps (mmdet GIoULoss default 1e-6) */
+  float grad_scale;        /* dL_total / d(sum_i w_i * loss_i), e.g. loss_weight / avg_factor */
+  /* outputs (any may be NULL) */
+  float* box2d;            /* [n, 4] */
+  uint8_t* valid;          /* [n] KITTI_CAM validity (kitti_dataset_GGA_match.py:741-748), else 1 */
+  uint8_t* argidx;         /* [n, 4] corner index attaining (xmin, ymin, xmax, ymax), first wins */
+  float* loss;             /* [n] unweighted per-box loss (L1: [n, 4] per side) */
+  float* loss_sum;         /* [1]  sum_i w_i * loss_i  (deterministic order) */
+  float* grad_boxes;       /* [n, 7] d(total)/d(boxes) */
+  float* grad_box2d;       /* [n, 4] d(total)/d(box2d) */
+  float* grad_target;      /* [n, 4] d(total)/d(target) (PGD passes a prediction as target) */
+} gga_box_loss_args;
+
+int gga_box_project_loss(const gga_box_loss_args* args, void* stream);
+
+/* Backward of the projection alone: grad_boxes[n,7] from grad_box2d[n,4] and the saved
+ * argidx (torch routes the gradient of min/max(dim) to the single returned index). */
+int gga_box_project_backward(const float* boxes, const float* proj, int proj_stride,
+                             const float* rt, int rt_stride, const int32_t* frame_of_box,
+                             const uint8_t* argidx, const float* grad_box2d, float* grad_boxes,
+                             int n, int mode, float depth_clamp, void* stream);
+
+/* 2D loss on given boxes (no projection): per-box loss, weighted sum, gradients. */
+int gga_box2d_loss(const float* pred, const float* target, const float* weight, int weight_cols,
+                   const float* grad_loss, int n, int loss_kind, float eps, float grad_scale,
+                   float* loss, float* loss_sum, float* grad_pred, float* grad_target, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Matching — block-diagonal pairwise 2D IoU + argmax (pseudo-label matching).
+ * Mirrors image_box_overlap (/root/reference/mmdet3d/core/evaluation/kitti_utils/eval.py:85-114,
+ * criterion -1) as called with dt first by tools/utils_pseudo_labels_gga.py:45, followed by
+ * np.argmax(axis=-1) (:60, first maximum wins).  Only the per-frame diagonal blocks that
+ * calculate_iou_partly (eval.py:402-416) keeps are computed.
+ *   dt : float32 [sum_dt, 4] (projected boxes), dt_offsets int32 [F+1]
+ *   gt : float64 [sum_gt, 4] (annotation boxes), gt_offsets int32 [F+1]
+ *   match : int32 [sum_dt] index into the frame's gt list (-1 if the frame has no gt)
+ *   best_iou : float32 [sum_dt] (the float32 the reference's overlaps array holds)
+ *   overlaps : optional float32, the concatenated row-major blocks [n_dt_f, n_gt_f]
+ *              at ov_offsets int64 [F+1]
+ * ---------------------------------------------------------------------------------- */
+int gga_match_dt_gt(const float* dt, const int32_t* dt_offsets, const double* gt,
+                    const int32_t* gt_offsets, int num_frames, int32_t* match, float* best_iou,
+                    float* overlaps, const int64_t* ov_offsets, void* stream);
+
+/* Dense pairwise IoU of the same function in float64: out [N, K]. */
+int gga_image_box_overlap_f64(const double* boxes, int N, const double* query, int K,
+                              int criterion, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Test hooks (device build of include/gga_detmath.h and of the per-box preparation).
+ * ---------------------------------------------------------------------------------- */
+int gga_test_sincos(const float* x, int64_t n, float* sn, float* cs, void* stream);
+/* prep : float [num_boxes, 8] = (cx, cy, cz_centre, hz, cosa, sina, hx, hy) */
+int gga_test_box_prep(const float* boxes, int num_boxes, float* prep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGA_B200_H_ */
