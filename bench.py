@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — GGA geometry hot path: membership + projection + IoU/GIoU loss fwd+bwd, frames/s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank/GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "GGA KITTI training shape"): 8 frames per GPU per step,
+120 000 LiDAR points (x,y,z,r) and 256 3D proposals per frame, KITTI-000000 calib, GIoU
+consistency loss against 2D targets, forward + backward to the box parameters.  Synthetic
+data (gga_b200/synth.py).  One "step" = one pass of the hot path over one
+batch of 8 frames.  Frames shard across ranks with no data-path collective ("weak" scaling);
+the only exchange is the scalar all-reduce of the loss sum (the reference's reduce_mean /
+_parse_losses), issued asynchronously.
+
+Prints ONE JSON line (rank 0).  Keys: see DESIGN.md §6.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = 2
+METRIC = 'geometry_loss_fwd_bwd_frames_per_s'
+UNIT = 'frames/s'
+L2_BYTES = 126 * 1024 * 1024
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def step_bytes(F, N, M, W):
+    """Algorithmic bytes of one step (SURVEY.md §8d / BASELINE.md §3)."""
+    member = F * (16 * N + 28 * M + 4 * N * W)
+    boxes = F * M * ((28 + 64 + 16 + 16) + 32)
+    return member, member + boxes
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.004):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def sample(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                nv, 'nvmlDeviceGetCurrentClocksEventReasons') else int(
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown',
+                     0x4: 'sw_power_cap', 0x80: 'hw_power_brake_slowdown'}
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        while not self._stop.is_set():
+            self.sample()
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': 0}
+        return {'sm_mhz': int(np.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        try:
+            return int(vis.split(',')[local])
+        except Exception:
+            return local
+    return local
+
+
+# ----------------------------------------------------------------------------- CPU reference path
+def cpu_frame_fn(nthreads):
+    """Returns f(frame_dict, n_points) running the reference's CPU path for one frame:
+    points_in_boxes_cpu (oracle/pib_oracle.c, the literal mmcv loop) + torch-CPU corners ->
+    lidar2img -> min/max -> GIoU loss -> backward (oracle/geometry.py, oracle/losses.py)."""
+    import torch
+    from oracle import geometry as og
+    from oracle import losses as ol
+    from oracle import membership as om
+    om.build()
+    torch.set_num_threads(max(1, nthreads))
+
+    def run(f, n_points):
+        pts = f['points'][:n_points]
+        mask = om.points_in_boxes_all_np(pts, f['boxes'], nthreads=nthreads)
+        M = f['boxes'].shape[0]
+        b = torch.from_numpy(f['boxes']).clone().requires_grad_(True)
+        l2i = torch.from_numpy(f['lidar2img'])[None].expand(M, 4, 4)
+        box2d = og.project_lidar_direct(b, l2i)
+        loss = ol.giou_loss_module(box2d, torch.from_numpy(f['target']), torch.from_numpy(f['weight']),
+                                   avg_factor=float(M))
+        loss.backward()
+        return int(mask.sum()), float(loss)
+    return run
+
+
+def time_cpu_baseline(synth, budget_s=12.0):
+    nthreads = os.cpu_count() or 1
+    run = cpu_frame_fn(nthreads)
+    c = synth.CONFIGS[CFG]
+    f = synth.make_frame(CFG, 900000)
+    run(f, c['N'])  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while True:
+        run(f, c['N'])
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or n >= 50:
+            break
+    return {'value': round(n / dt, 3), 'unit': UNIT, 'cores': nthreads, 'kind': 'port',
+            'sample': f'{n} full frames of {c["N"]} pts x {c["M"]} boxes (oracle/pib_oracle.c with '
+                      f'{nthreads} OpenMP threads + torch-CPU projection/GIoU fwd+bwd), {dt:.1f} s'}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from gga_b200 import synth
+    nthreads = os.cpu_count() or 1
+    run = cpu_frame_fn(nthreads)
+    c = synth.CONFIGS[CFG]
+    N, M = c['N'], c['M']
+    frames = [synth.make_frame(CFG, 900000 + i) for i in range(2)]
+    run(frames[0], N)
+    t0 = time.perf_counter()
+    run(frames[1], N)
+    t1 = time.perf_counter() - t0
+    total = args.steps + args.warmup
+    frac = min(1.0, 150.0 / max(total * t1, 1e-9))
+    n_pts = int(max(2000, min(N, round(frac * N))))
+    for i in range(args.warmup):
+        run(frames[i % 2], n_pts)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        run(frames[i % 2], n_pts)
+    dt = time.perf_counter() - t0
+    fps = args.steps * (n_pts / N) / dt
+    sample = (f'each step = first {n_pts} of {N} points x {M} boxes of one frame (membership) + all {M} '
+              f'boxes projection/GIoU fwd+bwd; frames counted as {n_pts}/{N} per step')
+    out = {
+        'impl': 'reference', 'metric': METRIC, 'value': round(fps, 3), 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(dt / max(args.steps, 1) * 1e3, 4),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(c, args.gpus),
+        'cpu_baseline': {'value': round(fps, 3), 'unit': UNIT, 'cores': nthreads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': round(fps, 3), 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(c, n_gpus):
+    return {'workload': 'gga_kitti_train (BASELINE.json configs[1])', 'frames_per_gpu_per_step': c['frames_per_gpu'],
+            'points_per_frame': c['N'], 'boxes_per_frame': c['M'], 'loss': 'giou(lidar_direct projection), fwd+bwd',
+            'global_frames_per_step': c['frames_per_gpu'] * n_gpus, 'parallelism': f'frames sharded x{n_gpus}'}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    import gga_b200 as G
+    from gga_b200 import synth
+    from gga_b200.step import GeometryStep
+
+    c = synth.CONFIGS[CFG]
+    F, N, M = c['frames_per_gpu'], c['N'], c['M']
+    W = G.row_words(M)
+    member_bytes, all_bytes = step_bytes(F, N, M, W)
+    n_sets = max(3, -(-2 * L2_BYTES // all_bytes) + 1)   # rotating working set > 2x L2
+    # synthetic frames: 2 distinct host batches per rank, replicated into n_sets device sets
+    host = [synth.make_batch(CFG, 100000 * rank + 16 * k, F) for k in range(2)]
+    sets, steps = [], []
+    for k in range(n_sets):
+        hb = host[k % 2]
+        t = {name: torch.from_numpy(np.ascontiguousarray(hb[name])).to(dev)
+             for name in ('points', 'boxes', 'lidar2img', 'target', 'weight')}
+        sets.append(t)
+        s = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
+        s.capture(t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
+        steps.append(s)
+    torch.cuda.synchronize()
+
+    comm = torch.cuda.Stream() if world > 1 else None
+    red = torch.zeros((n_sets, 1), dtype=torch.float32, device=dev)
+    pending = []
+
+    def one_step(i):
+        s = steps[i % n_sets]
+        s.replay()
+        if world > 1:   # loss scalar all-reduce (reduce_mean / _parse_losses), off the critical path
+            ev = torch.cuda.Event()
+            ev.record()
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                red[i % n_sets].copy_(s.loss_sum)
+                pending.append(dist.all_reduce(red[i % n_sets], async_op=True))
+            if len(pending) > 64:
+                pending.pop(0).wait()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(physical_gpu_index(local))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        one_step(i)
+    e1.record()
+    sampler.sample()
+    if comm is not None:
+        torch.cuda.current_stream().wait_stream(comm)
+    barrier()
+    sampler.stop()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        for p in pending:
+            p.wait()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * F * args.steps / (ms * 1e-3)
+
+    # dominant kernel alone (membership), same rotation of buffers, CUDA events on the launch stream
+    L = G._lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    kreps = max(50, min(args.steps, 500))
+
+    def member(i):
+        t, s = sets[i % n_sets], steps[i % n_sets]
+        rc = L.gga_points_in_boxes_bits(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), s.bits.data_ptr(), F, N, M, st)
+        assert rc == 0
+    for i in range(5):
+        member(i)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for i in range(kreps):
+        member(i)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / kreps
+    peak, peak_src = peaks()
+    achieved = member_bytes / (kernel_ms * 1e-3) / 1e9
+
+    # end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    hb = host[0]
+    hin = {name: torch.from_numpy(np.ascontiguousarray(hb[name])).pin_memory()
+           for name in ('points', 'boxes', 'lidar2img', 'target', 'weight')}
+    es = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
+    eargs = (hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'], float(F * M))
+    for _ in range(3):
+        es.run_host(*eargs)
+    ereps = max(5, min(args.steps, 40))
+    barrier()
+    x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    x0.record()
+    for _ in range(ereps):
+        es.run_host(*eargs)
+    x1.record()
+    barrier()
+    ems = x0.elapsed_time(x1)
+    if world > 1:
+        t = torch.tensor([ems], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+    h2d, d2h = es.host_bytes(*eargs[:5])
+    e2e = {'value': round(world * F * ereps / (ems * 1e-3), 1), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+           'd2h_bytes_per_step': int(d2h), 'steps': ereps, 'ms_per_step': round(ems / ereps, 4)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = time_cpu_baseline(synth)
+
+    if rank == 0:
+        cfg = workload_config(c, world)
+        cfg['l2'] = f'rotating {n_sets} input/output sets ({n_sets * all_bytes / 1e6:.0f} MB > 2x 126 MB L2)'
+        cfg['launch'] = 'CUDA graph replay per step'
+        out = {
+            'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_per_step, 5), 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+            'roofline': {'bound': 'hbm', 'kernel': 'pib_kernel (membership, bit-packed)', 'achieved': round(achieved, 1),
+                         'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4), 'traffic': None,
+                         'peak_source': peak_src, 'kernel_ms': round(kernel_ms, 5),
+                         'algorithmic_bytes_per_launch': member_bytes,
+                         'step_frac_of_hbm_roofline': round(all_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': 2 * args.steps,
+            'clocks': sampler.summary(),
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

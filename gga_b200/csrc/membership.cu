@@ -501,13 +501,15 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   GGA_REQUIRE(B >= 0 && num_points >= 0 && num_boxes >= 0, "negative size");
   GGA_REQUIRE(pts_stride >= 3, "pts_stride must be >= 3 (got %d)", pts_stride);
   if (B == 0 || num_points == 0) return GGA_OK;
-  GGA_REQUIRE(points && out, "null points/out pointer");
   cudaStream_t st = gga_stream(stream);
   if (num_boxes == 0) {
-    if (mode == kModePart)  // every point is in no box
+    if (mode == kModePart) {  // every point is in no box
+      GGA_REQUIRE(out, "null out pointer");
       GGA_CHECK_CUDA(cudaMemsetAsync(out, 0xff, (size_t)B * num_points * sizeof(int32_t), st));
-    return GGA_OK;  // bits / all have zero-width rows
+    }
+    return GGA_OK;  // bits / all have zero-width rows (the output buffer is empty)
   }
+  GGA_REQUIRE(points && out, "null points/out pointer");
   GGA_REQUIRE(boxes, "null boxes pointer");
   GGA_REQUIRE(B <= 65535, "at most 65535 frames per call (got %d)", B);
 

@@ -1,0 +1,125 @@
+"""One training-shaped step of the geometry hot path over a batch of frames:
+
+    membership masks (bit-packed)  +  3D box -> 2D box projection  +  IoU/GIoU/L1 loss
+    forward AND backward to the box parameters,
+
+i.e. what a GGA head does per iteration with ``points_in_boxes_all``
+(``/root/reference/mmdet3d/core/bbox/structures/base_box3d.py:539-568``),
+``get_prediction_single`` (``mmdet3d/models/dense_heads/centerpoint_head_gga.py:250-341``) and
+the consistency loss (``pgd_head.py:744-748`` / ``centerpoint_head_gga.py:714-720``) followed by
+``loss.backward()``.  The step talks to the C ABI directly (no autograd graph): the loss
+kernel emits ``d loss / d boxes`` in the same launch, scaled by ``loss_weight / avg_factor``
+(mmdet ``weight_reduce_loss``).
+
+``GeometryStep`` owns the output buffers of one batch shape so that a step is allocation
+free and can be captured in a CUDA graph (``capture()`` / ``replay()``).
+``GeometryStep.run_host`` is the same step for HOST buffers (pinned numpy / torch CPU
+tensors): H2D copies, the kernels, and D2H of masks, loss and gradients.
+"""
+import torch
+
+from . import _lib
+from .losses import KINDS
+from .project import MODES
+
+
+class GeometryStep:
+
+    def __init__(self, num_frames, num_points, num_boxes, device, pts_stride=4, kind='giou',
+                 mode='lidar_direct', loss_weight=1.0, eps=1e-6, depth_clamp=0.1):
+        self.F, self.N, self.M = int(num_frames), int(num_points), int(num_boxes)
+        self.device = torch.device(device)
+        self.pts_stride = int(pts_stride)
+        self.kind = KINDS[kind]
+        self.mode = MODES[mode]
+        self.loss_weight, self.eps, self.depth_clamp = float(loss_weight), float(eps), float(depth_clamp)
+        L = _lib.load()
+        self.L = L
+        self.W = L.gga_pib_row_words(self.M)
+        dev = self.device
+        n = self.F * self.M
+        self.bits = torch.empty((self.F, self.N, self.W), dtype=torch.int32, device=dev)
+        self.box2d = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        self.loss = torch.empty((n, 4 if self.kind == _lib.LOSS_L1 else 1), dtype=torch.float32, device=dev)
+        self.loss_sum = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.grad_boxes = torch.empty((n, 7), dtype=torch.float32, device=dev)
+        self.graph = None
+        self._host = None
+
+    # ------------------------------------------------------------------ device-resident step
+    def run(self, points, boxes, lidar2img, target, weight=None, avg_factor=None, stream=None):
+        """points [F,N,pts_stride], boxes [F,M,7], lidar2img [F,M,4,4] (one calib per object,
+        the GGA_lidar2img layout) or [4,4], target [F,M,4], weight [F,M] — contiguous fp32 CUDA
+        tensors.  Enqueues the step on the current stream; returns nothing (results are in
+        ``self.bits / box2d / loss / loss_sum / grad_boxes``; ``loss_sum`` is the weighted SUM,
+        gradients are already scaled by ``loss_weight / avg_factor``)."""
+        L = self.L
+        n = self.F * self.M
+        st = _lib.current_stream(self.device) if stream is None else stream
+        _lib.check(L.gga_points_in_boxes_bits(points.data_ptr(), self.pts_stride, boxes.data_ptr(),
+                                              self.bits.data_ptr(), self.F, self.N, self.M, st),
+                   'points_in_boxes_bits')
+        a = _lib.BoxLossArgs()
+        a.boxes = boxes.data_ptr()
+        a.proj = lidar2img.data_ptr()
+        a.proj_stride = 16 if lidar2img.dim() > 2 else 0
+        a.target = target.data_ptr()
+        if weight is not None:
+            a.weight, a.weight_cols = weight.data_ptr(), 1
+        a.n, a.mode, a.loss_kind = n, self.mode, self.kind
+        a.depth_clamp, a.eps = self.depth_clamp, self.eps
+        a.grad_scale = self.loss_weight / float(avg_factor if avg_factor is not None else max(n, 1))
+        a.box2d, a.loss, a.loss_sum = self.box2d.data_ptr(), self.loss.data_ptr(), self.loss_sum.data_ptr()
+        a.grad_boxes = self.grad_boxes.data_ptr()
+        _lib.check(L.gga_box_project_loss(a, st), 'box_project_loss')
+
+    def capture(self, *args, **kw):
+        """Warm up, then capture ``run(*args)`` into a CUDA graph (inputs are baked in by address)."""
+        with torch.cuda.device(self.device):
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self.run(*args, **kw)   # lazy initialisation must not happen under capture
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.run(*args, **kw)
+            self.graph = g
+        return g
+
+    def replay(self):
+        self.graph.replay()
+
+    # ------------------------------------------------------------------ host-buffer step
+    def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None):
+        """Same step with HOST inputs (pinned torch CPU tensors) and HOST results: returns
+        (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous."""
+        dev = self.device
+        if self._host is None:
+            h = {}
+            for name, t in (('points', points), ('boxes', boxes), ('lidar2img', lidar2img),
+                            ('target', target), ('weight', weight)):
+                h['d_' + name] = torch.empty(t.shape, dtype=t.dtype, device=dev)
+            h['h_bits'] = torch.empty(self.bits.shape, dtype=torch.int32).pin_memory()
+            h['h_grad'] = torch.empty(self.grad_boxes.shape, dtype=torch.float32).pin_memory()
+            h['h_loss'] = torch.empty((1,), dtype=torch.float32).pin_memory()
+            self._host = h
+        h = self._host
+        h['d_points'].copy_(points, non_blocking=True)
+        h['d_boxes'].copy_(boxes, non_blocking=True)
+        h['d_lidar2img'].copy_(lidar2img, non_blocking=True)
+        h['d_target'].copy_(target, non_blocking=True)
+        h['d_weight'].copy_(weight, non_blocking=True)
+        self.run(h['d_points'], h['d_boxes'], h['d_lidar2img'], h['d_target'], h['d_weight'], avg_factor)
+        h['h_bits'].copy_(self.bits, non_blocking=True)
+        h['h_grad'].copy_(self.grad_boxes, non_blocking=True)
+        h['h_loss'].copy_(self.loss_sum, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return h['h_bits'], float(h['h_loss'][0]), h['h_grad']
+
+    def host_bytes(self, points, boxes, lidar2img, target, weight):
+        """(h2d, d2h) bytes moved by one ``run_host``."""
+        h2d = sum(t.numel() * t.element_size() for t in (points, boxes, lidar2img, target, weight))
+        d2h = self.bits.numel() * 4 + self.grad_boxes.numel() * 4 + 4
+        return h2d, d2h
