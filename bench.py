@@ -289,7 +289,8 @@ def run_ours(args):
 
     def member(i):
         t, s = sets[i % n_sets], steps[i % n_sets]
-        rc = L.gga_points_in_boxes_bits(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), s.bits.data_ptr(), F, N, M, st)
+        rc = L.gga_points_in_boxes_bits(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), s.bits.data_ptr(), F, N, M,
+                                        s.ws.data_ptr(), s.ws.numel(), st)
         assert rc == 0
     for i in range(5):
         member(i)

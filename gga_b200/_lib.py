@@ -38,9 +38,14 @@ SIGNATURES = {
     'gga_last_error': ([], ctypes.c_char_p),
     'gga_device_info': ([ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(ctypes.c_size_t)], c_int),
     'gga_pib_row_words': ([c_int], c_int),
-    'gga_points_in_boxes_bits': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
-    'gga_points_in_boxes_all': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
-    'gga_points_in_boxes_part': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    'gga_pib_workspace_bytes': ([c_int, c_int, c_int], ctypes.c_size_t),
+    'gga_pib_workspace_init': ([c_void_p, ctypes.c_size_t, c_void_p], c_int),
+    'gga_points_in_boxes_bits': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  ctypes.c_size_t, c_void_p], c_int),
+    'gga_points_in_boxes_all': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                 ctypes.c_size_t, c_void_p], c_int),
+    'gga_points_in_boxes_part': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  ctypes.c_size_t, c_void_p], c_int),
     'gga_points_in_boxes_all_host': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int], c_int),
     'gga_pib_set_tuning': ([c_int, c_int], c_int),
     'gga_box_project_loss': ([ctypes.POINTER(BoxLossArgs), c_void_p], c_int),

@@ -5,17 +5,25 @@
 // /root/reference/mmdet3d/ops/__init__.py:12-13, called from
 // /root/reference/mmdet3d/core/bbox/structures/base_box3d.py:534,566).
 //
-// Design: the brute-force test is FP32-issue bound (14 instr x N x T), the
-// output is HBM bound (16 B in, 4*W B out per point).  To sit on the HBM roofline each
-// persistent CTA (one per SM) first builds, in shared memory,
-//   (1) the per-box derived terms (centre z, half extents, cos/sin of -rz evaluated in
-//       double with the deterministic routine of include/gga_detmath.h), and
-//   (2) a BEV cull grid: for every cell a bit mask of the boxes whose conservatively
-//       inflated bounding rectangle touches the cell,
-// then streams its slice of points: one lane per (point, 256-box group), cell lookup, exact
-// test only for the candidate bits, and 32 B of packed mask per lane written as two fully
-// coalesced 512 B warp stores after a shuffle transpose.  Culling never changes the result:
-// a box is a candidate wherever a point could pass the exact fp32 test.
+// Design.  The brute-force test is FP32-issue bound (14 instr x N x T); the
+// useful traffic is 16 B in and 4*W B out per point.  To sit on the HBM roofline the work is
+// split in two launches chained with programmatic dependent launch (PDL):
+//
+//  1. pib_prep_kernel — once per frame, a few CTAs per frame: the per-box contract terms
+//     (centre z, half extents, cos/sin of -rz from the deterministic double routine of
+//     include/gga_detmath.h) and a BEV "frame index": a G x G grid whose 32-bit cell word is
+//     empty / one candidate box id / (count, offset) into a packed id list.  Boxes are
+//     rasterised conservatively (AABB of the inflated rotated footprint refined by a
+//     separating-axis test per cell), so a box is listed wherever a point could pass the
+//     exact fp32 test; G is chosen per frame so that the lists fit their pool.
+//  2. pib_stream_kernel — a persistent grid of light CTAs (256 threads, 6 per SM) streams the
+//     points: one LDG.128 per point, one L1-cached cell-word lookup, the exact test only for
+//     the listed candidates, and the packed mask rows staged per warp in shared memory so
+//     that every warp store is a fully coalesced 512 B STG.128.  Warps take 4-batch tiles
+//     from per-range counters (ranges follow blockIdx % R so that CTAs sharing an SM share a
+//     frame's index in L1) and steal from neighbouring ranges at the end.
+//
+// Culling never changes the result; every candidate is decided by inside_box() below.
 #include <float.h>
 
 #include "../../include/gga_detmath.h"
@@ -23,22 +31,20 @@
 
 namespace {
 
-constexpr int kThreads = 1024;
-constexpr int kMaxGrid = 128;  // cells per side (7 bits in the packed range)
+constexpr int kStreamThreads = 256;
+constexpr int kWarps = kStreamThreads / 32;
+constexpr int kOcc = 5;  // stream CTAs per SM (48 registers per thread)
+constexpr int kPrepThreads = 256;
+constexpr int kMaxSliceCells = 4096;
+constexpr int kMaxG = 256;
+constexpr uint32_t kCntShift = 22;
+constexpr uint32_t kPayMask = (1u << kCntShift) - 1u;
+constexpr uint32_t kCntLong = 1023u;        // count field value meaning "real count is ids[payload]"
+constexpr uint32_t kCellAll = 0xffffffffu;  // every box is a candidate (pool overflow fallback)
+constexpr uint32_t kMaxCap = kPayMask - 1u;
+constexpr int kMaxBoxes = 32767;
 
-struct PibParams {
-  const float* points;
-  const float* boxes;
-  void* out;
-  long long items_per_frame;  // num_points * groups
-  int pts_stride;
-  int num_points;
-  int num_boxes;
-  int row_words;  // words per point row (Wp)
-  int groups;     // lanes per point (row_words / WL)
-  int G;          // cull grid cells per side
-  int vec4;       // points are 16 B aligned float4
-};
+enum { kModeBits = 0, kModeAll = 1, kModePart = 2 };
 
 struct BoxPrep {
   float cx, cy, cz, hz;      // centre (z already shifted to the box centre), z half extent
@@ -83,11 +89,9 @@ __device__ __forceinline__ bool inside_box(float x, float y, float z, const floa
 // A point that passes the fp32 test has |p - c| within the rotated half extents up to a
 // relative 1e-6 (rounding of the shifts, products and of cos/sin); the rectangle is
 // inflated by 2^-13 of its size and every bound is rounded outwards.
-__device__ __forceinline__ int box_rect(const float4 a, const float4 r, float& x0, float& x1,
-                                        float& y0, float& y1) {
-  const float cosa = r.x, sina = r.y, hx = r.z, hy = r.w;
-  if (!(hx > 0.f) || !(hy > 0.f) || !(cosa == cosa) || !(sina == sina) || !isfinite(a.x) ||
-      !isfinite(a.y))
+__device__ __forceinline__ int box_rect(float cx, float cy, float cosa, float sina, float hx, float hy,
+                                        float& x0, float& x1, float& y0, float& y1) {
+  if (!(hx > 0.f) || !(hy > 0.f) || !(cosa == cosa) || !(sina == sina) || !isfinite(cx) || !isfinite(cy))
     return 0;
   const float ac = fabsf(cosa), as = fabsf(sina);
   float ex = __fadd_ru(__fmul_ru(ac, hx), __fmul_ru(as, hy));
@@ -95,12 +99,33 @@ __device__ __forceinline__ int box_rect(const float4 a, const float4 r, float& x
   const float m = __fmul_ru(__fadd_ru(ex, ey), 1.220703125e-4f);
   ex = __fadd_ru(ex, m);
   ey = __fadd_ru(ey, m);
-  x0 = __fsub_rd(a.x, ex);
-  x1 = __fadd_ru(a.x, ex);
-  y0 = __fsub_rd(a.y, ey);
-  y1 = __fadd_ru(a.y, ey);
+  x0 = __fsub_rd(cx, ex);
+  x1 = __fadd_ru(cx, ex);
+  y0 = __fsub_rd(cy, ey);
+  y1 = __fadd_ru(cy, ey);
   if (!isfinite(x0) || !isfinite(x1) || !isfinite(y0) || !isfinite(y1)) return 2;
   return 1;
+}
+
+// What the rasteriser needs of a box.  fp32 sincosf instead of the double-precision contract
+// terms: the index only has to be conservative, and the 2^-13 inflation dwarfs the ~1e-7
+// difference between sincosf and the exactly rounded cos/sin.
+struct RasterBox {
+  int kind;
+  float cx, cy, cs, sn, hx, hy;
+  float x0, x1, y0, y1;
+};
+
+__device__ __forceinline__ RasterBox raster_box(const float* __restrict__ b) {
+  RasterBox r;
+  r.cx = b[0];
+  r.cy = b[1];
+  r.hx = __fmul_ru(b[3], 0.5f);
+  r.hy = __fmul_ru(b[4], 0.5f);
+  sincosf(-b[6], &r.sn, &r.cs);
+  r.x0 = r.x1 = r.y0 = r.y1 = 0.f;
+  r.kind = box_rect(r.cx, r.cy, r.cs, r.sn, r.hx, r.hy, r.x0, r.x1, r.y0, r.y1);
+  return r;
 }
 
 __device__ __forceinline__ uint32_t f2ord(float f) {
@@ -111,350 +136,622 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-struct GridHdr {
-  float gx0, gy0, invx, invy, fmaxx, fmaxy;
-  uint32_t minx, miny, maxx, maxy;  // order-preserving encodings, reduced with atomics
-  int n_rect;
-  int degenerate;
+// Per-frame header of the index (48 B, written by slice 0 of the prep kernel).
+// The grid is (G + 2) x (G + 2): the inner G x G cells tile the bounding rectangle of all
+// finite footprints, the one-cell border catches everything outside it (and NaN), so points
+// and footprints go through ONE clamped, monotone cell function and no case is special.
+struct __align__(16) FrameHdr {
+  float gx0, gy0, invx, invy;  // padded cell = clamp(floor((v - g0) * inv + 1), 0, G + 1)
+  float cwx, cwy;              // inner cell size in metres (inf when the extent is degenerate)
+  float slopx, slopy;          // absolute slack of the cell geometry (rounding of the cell function)
+  int G, n_rect, n_inf, pad;
 };
 
-// Monotone non-decreasing in v (one rounded subtraction, one rounded product by a
-// non-negative constant): boxes and points go through the same function, so
-// rect.lo <= p <= rect.hi implies cell(rect.lo) <= cell(p) <= cell(rect.hi).
-__device__ __forceinline__ float fcell(float v, float g0, float inv) {
-  return __fmul_rn(__fsub_rn(v, g0), inv);
+// Monotone non-decreasing in v: one rounded subtraction, one rounded product by a
+// non-negative constant, one rounded addition, clamps, truncation.  Boxes and points go
+// through the same function, so rect.lo <= p <= rect.hi implies cell(rect.lo) <= cell(p) <=
+// cell(rect.hi).  NaN maps to the last cell (fminf returns the non-NaN operand).
+__device__ __forceinline__ int pcell(float v, float g0, float inv, float gp1) {
+  const float f = __fadd_rn(__fmul_rn(__fsub_rn(v, g0), inv), 1.0f);
+  return (int)fmaxf(fminf(f, gp1), 0.f);
 }
 
-template <int WL>
-__device__ __forceinline__ void load_cand(const uint32_t* row, uint32_t (&m)[WL]) {
-  if constexpr (WL == 8) {
-    const uint4 a = *reinterpret_cast<const uint4*>(row);
-    const uint4 b = *reinterpret_cast<const uint4*>(row + 4);
-    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-    m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
-  } else if constexpr (WL == 4) {
-    const uint4 a = *reinterpret_cast<const uint4*>(row);
-    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
-  } else if constexpr (WL == 2) {
-    const uint2 a = *reinterpret_cast<const uint2*>(row);
-    m[0] = a.x; m[1] = a.y;
-  } else {
-    m[0] = row[0];
-  }
-}
-
-enum { kModeBits = 0, kModeAll = 1, kModePart = 2 };
-
-// Dynamic shared memory layout (all 16 B aligned):
-//   float4  sbox[2 * T]                  box t at [2t] = (cx, cy, cz, hz), [2t+1] = (cosa, sina, hx, hy)
-//   uint32  table[(G*G + 1) * Wp]        candidate bit masks per cell (cell G*G = outside the grid)
-//   uint8   summ[(G*G + 1) * groups8]    per (cell, 8-word group): which of the 8 words are non-zero
-//   uint32  stage[32 warps * 256]        per-warp transpose buffer for the 32 B-per-lane stores
-struct SmemLayout {
-  size_t table_off, summ_off, stage_off, total;
+// Workspace layout (device memory owned by the caller, see gga_pib_workspace_bytes):
+//   uint32   ids_used[F]        allocation cursor of every frame's id pool; zero between calls
+//   FrameHdr hdr[F]
+//   float4   prep[F][2 T]       box t: [2t] = (cx, cy, cz, hz), [2t+1] = (cosa, sina, hx, hy)
+//   uint32   grid[F][gstride]   cell words, row-major (G + 2) x (G + 2) of the frame's own G
+//   uint16   ids[F][cap]
+struct WsLayout {
+  size_t ids_used, hdr, prep, grid, ids, total;
+  size_t gstride;  // words per frame
+  uint32_t cap;    // ids per frame
+  int Gmax;
 };
 
-__host__ __device__ inline SmemLayout smem_layout(int T, int G, int Wp, bool need_stage) {
-  SmemLayout L;
-  const size_t ncell = (size_t)G * G + 1;
-  const size_t groups8 = (size_t)(Wp + 7) / 8;
-  L.table_off = (size_t)T * 32;
-  L.summ_off = L.table_off + ((ncell * Wp * 4 + 15) & ~(size_t)15);
-  L.stage_off = L.summ_off + ((ncell * groups8 + 15) & ~(size_t)15);
-  L.total = L.stage_off + (need_stage ? (size_t)kThreads * 32 : 0);
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline WsLayout ws_layout(int F, int T, int Gmax) {
+  WsLayout L;
+  L.Gmax = Gmax;
+  L.gstride = align_up((size_t)(Gmax + 2) * (Gmax + 2), 4);
+  size_t cap = (size_t)8 * Gmax * Gmax;
+  if (cap < (size_t)16 * T + 64) cap = (size_t)16 * T + 64;
+  if (cap > kMaxCap) cap = kMaxCap;
+  cap = cap & ~(size_t)7;
+  L.cap = (uint32_t)cap;
+  size_t o = 0;
+  L.ids_used = o; o = align_up(o + (size_t)F * 4, 256);
+  L.hdr = o; o = align_up(o + (size_t)F * sizeof(FrameHdr), 256);
+  L.prep = o; o = align_up(o + (size_t)F * T * 32, 256);
+  L.grid = o; o = align_up(o + (size_t)F * L.gstride * 4, 256);
+  L.ids = o; o = align_up(o + (size_t)F * cap * 2, 256);
+  L.total = o;
   return L;
 }
 
-// Cheap conservative rectangle straight from the raw box (fp32 sincosf instead of the
-// double-precision contract terms): the cull grid only has to be conservative, and the
-// 2^-13 inflation of box_rect dwarfs the ~1e-7 difference between sincosf and the exact
-// rounded cos/sin.  This lets the grid be built while other warps are still in the long
-// double-precision dependency chain of prep_box.
-__device__ __forceinline__ int approx_rect(const float* __restrict__ b, float& x0, float& x1, float& y0,
-                                           float& y1) {
-  const float hx = __fmul_ru(b[3], 0.5f), hy = __fmul_ru(b[4], 0.5f);
-  float sn, cs;
-  sincosf(-b[6], &sn, &cs);
-  return box_rect(make_float4(b[0], b[1], 0.f, 0.f), make_float4(cs, sn, hx, hy), x0, x1, y0, y1);
+int g_tune_grid = 0, g_tune_occ = 0;
+
+inline int pick_gmax(int N, int T) {
+  if (g_tune_grid > 0) return g_tune_grid > kMaxG ? kMaxG : g_tune_grid;
+  double cells = 64.0 * (double)T;
+  if (cells > 4.0 * (double)N) cells = 4.0 * (double)N;
+  int G = (int)(sqrt(cells) + 0.5);
+  if (G < 4) G = 4;
+  if (G > 192) G = 192;
+  return G;
 }
 
-__device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+// ------------------------------------------------------------------------------------------
+// prep kernel
+// ------------------------------------------------------------------------------------------
+struct PrepParams {
+  const float* boxes;  // [F, T, 7]
+  unsigned char* ws;
+  WsLayout L;
+  int T;
+  int ncache;  // boxes whose raster terms are cached in shared memory
+};
+
+// Conservative "could a point of the INNER cell (tx, ty) (padded coordinates 1..G) pass the
+// exact test of this box": separating-axis test in the box frame.
+__device__ __forceinline__ bool sat_overlap(const RasterBox& rb, const FrameHdr& h, int tx, int ty) {
+  const float ccx = h.gx0 + ((float)tx - 0.5f) * h.cwx, ccy = h.gy0 + ((float)ty - 0.5f) * h.cwy;
+  const float dx = ccx - rb.cx, dy = ccy - rb.cy;
+  const float lx = dx * rb.cs - dy * rb.sn, ly = dx * rb.sn + dy * rb.cs;
+  const float Hx = 0.5f * h.cwx + h.slopx, Hy = 0.5f * h.cwy + h.slopy;
+  const float ac = fabsf(rb.cs), as = fabsf(rb.sn);
+  const float infl = (rb.hx + rb.hy + Hx + Hy) * 1.220703125e-4f;
+  const float bx = rb.hx + ac * Hx + as * Hy + infl, by = rb.hy + as * Hx + ac * Hy + infl;
+  return !(fabsf(lx) > bx) && !(fabsf(ly) > by);  // NaN / inf anywhere -> keep the box
 }
 
-// Builds boxes + cull grid + word summaries in shared memory.
-// Warp roles: the last `prep_warps` warps evaluate the exact per-box contract terms
-// (double-precision chain, ~2k cycles of latency), the others build the grid concurrently.
-__device__ void build_tables(const PibParams& p, const float* __restrict__ boxes, float4* sbox,
-                             uint32_t* table, uint32_t* summ32, GridHdr* hdr) {
-  const int T = p.num_boxes, G = p.G, Wp = p.row_words;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ncell = G * G + 1;
-  const int groups8 = (Wp + 7) >> 3;
-  int prep_warps = (T + 31) >> 5;
-  prep_warps = prep_warps < 1 ? 1 : (prep_warps > 16 ? 16 : prep_warps);
-  const int build_warps = kThreads / 32 - prep_warps;
-  const int nb = build_warps * 32;
+__device__ __forceinline__ void cell_range(const RasterBox& rb, const FrameHdr& h, int& cx0, int& cx1, int& cy0,
+                                           int& cy1) {
+  const int G = h.G;
+  cx0 = 0; cy0 = 0; cx1 = G + 1; cy1 = G + 1;
+  if (rb.kind == 1) {
+    const float gp1 = (float)(G + 1);
+    cx0 = pcell(rb.x0, h.gx0, h.invx, gp1);
+    cx1 = pcell(rb.x1, h.gx0, h.invx, gp1);
+    cy0 = pcell(rb.y0, h.gy0, h.invy, gp1);
+    cy1 = pcell(rb.y1, h.gy0, h.invy, gp1);
+  }
+}
 
-  if (warp >= build_warps) {
-    // ---- exact per-box terms (independent of the grid) ----
-    for (int t = tid - nb; t < T; t += prep_warps * 32) {
-      const BoxPrep q = prep_box(boxes + (long long)t * 7);
-      sbox[2 * t] = make_float4(q.cx, q.cy, q.cz, q.hz);
-      sbox[2 * t + 1] = make_float4(q.cosa, q.sina, q.hx, q.hy);
+constexpr int kBoxWords = 11;
+
+__global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams p) {
+  // let the dependent stream kernel start its prologue right away
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  extern __shared__ __align__(16) unsigned char dsm[];
+  uint32_t* cf = reinterpret_cast<uint32_t*>(dsm);                            // count | fill << 16
+  uint32_t* word = cf + (kMaxSliceCells + 4);                                 // offsets, then cell words
+  uint16_t* mine = reinterpret_cast<uint16_t*>(word + (kMaxSliceCells + 4));  // [T] boxes touching this slice
+  float* cbox = reinterpret_cast<float*>(dsm + (size_t)2 * (kMaxSliceCells + 4) * 4 + align_up((size_t)p.T * 2, 16));
+  __shared__ uint32_t s_minx, s_miny, s_maxx, s_maxy;
+  __shared__ int s_nrect, s_ninf, s_nmine, s_overflow;
+  __shared__ float s_sw[kPrepThreads / 32], s_sh[kPrepThreads / 32], s_swh[kPrepThreads / 32];
+  __shared__ FrameHdr s_hdr;
+  __shared__ uint32_t s_base, s_warp_tot[kPrepThreads / 32];
+
+  constexpr int kNW = kPrepThreads / 32;
+  const int T = p.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int f = blockIdx.y, slice = blockIdx.x, S = gridDim.x;
+  const float* __restrict__ boxes = p.boxes + (size_t)f * T * 7;
+  unsigned char* ws = p.ws;
+  uint32_t* ids_used = reinterpret_cast<uint32_t*>(ws + p.L.ids_used) + f;
+  float4* prep = reinterpret_cast<float4*>(ws + p.L.prep) + (size_t)f * 2 * T;
+  uint32_t* grid = reinterpret_cast<uint32_t*>(ws + p.L.grid) + (size_t)f * p.L.gstride;
+  uint16_t* ids = reinterpret_cast<uint16_t*>(ws + p.L.ids) + (size_t)f * p.L.cap;
+  const int ncache = p.ncache;
+
+  auto get_box = [&](int t) -> RasterBox {
+    if (t < ncache) {
+      const float* c = cbox + t * kBoxWords;
+      RasterBox r;
+      r.x0 = c[0]; r.x1 = c[1]; r.y0 = c[2]; r.y1 = c[3];
+      r.cx = c[4]; r.cy = c[5]; r.cs = c[6]; r.sn = c[7]; r.hx = c[8]; r.hy = c[9];
+      r.kind = __float_as_int(c[10]);
+      return r;
     }
+    return raster_box(boxes + (size_t)t * 7);
+  };
+
+  if (tid == 0) {
+    s_minx = s_miny = 0xffffffffu;
+    s_maxx = s_maxy = 0u;
+    s_nrect = s_ninf = s_nmine = s_overflow = 0;
+  }
+  __syncthreads();
+
+  // ---- pass A (warps 0..6): footprints, their extent, and the sums that predict the list
+  //      length; warp 7 meanwhile evaluates the exact contract terms of this slice's boxes ----
+  if (warp == kNW - 1) {
+    const int per = (T + S - 1) / S;
+    const int t0 = min(T, slice * per), t1 = min(T, t0 + per);
+    for (int t = t0 + lane; t < t1; t += 32) {
+      const BoxPrep q = prep_box(boxes + (size_t)t * 7);
+      prep[2 * t] = make_float4(q.cx, q.cy, q.cz, q.hz);
+      prep[2 * t + 1] = make_float4(q.cosa, q.sina, q.hx, q.hy);
+    }
+    if (lane == 0) s_sw[warp] = s_sh[warp] = s_swh[warp] = 0.f;
   } else {
-    // ---- cull grid ----
-    if (tid == 0) {
-      hdr->minx = hdr->miny = 0xffffffffu;
-      hdr->maxx = hdr->maxy = 0u;
-      hdr->n_rect = 0;
-      hdr->degenerate = 0;
-    }
-    {  // zero table and summaries (contiguous, sizes padded to 16 B)
-      uint4* t4 = reinterpret_cast<uint4*>(table);
-      const int n4 = (int)((reinterpret_cast<unsigned char*>(summ32) - reinterpret_cast<unsigned char*>(table)) >> 4) +
-                     ((ncell * groups8 + 15) >> 4);
-      for (int i = tid; i < n4; i += nb) t4[i] = make_uint4(0, 0, 0, 0);
-    }
-    bar_sync_named(1, nb);
-    for (int t = tid; t < T; t += nb) {
-      float x0, x1, y0, y1;
-      if (approx_rect(boxes + (long long)t * 7, x0, x1, y0, y1) == 1) {
-        atomicMin(&hdr->minx, f2ord(x0));
-        atomicMax(&hdr->maxx, f2ord(x1));
-        atomicMin(&hdr->miny, f2ord(y0));
-        atomicMax(&hdr->maxy, f2ord(y1));
-        atomicAdd(&hdr->n_rect, 1);
+    float sw = 0.f, sh = 0.f, swh = 0.f;
+    for (int t = tid; t < T; t += kPrepThreads - 32) {
+      const RasterBox rb = raster_box(boxes + (size_t)t * 7);
+      if (t < ncache) {
+        float* c = cbox + t * kBoxWords;
+        c[0] = rb.x0; c[1] = rb.x1; c[2] = rb.y0; c[3] = rb.y1;
+        c[4] = rb.cx; c[5] = rb.cy; c[6] = rb.cs; c[7] = rb.sn; c[8] = rb.hx; c[9] = rb.hy;
+        c[10] = __int_as_float(rb.kind);
+      }
+      if (rb.kind == 1) {
+        atomicMin(&s_minx, f2ord(rb.x0));
+        atomicMax(&s_maxx, f2ord(rb.x1));
+        atomicMin(&s_miny, f2ord(rb.y0));
+        atomicMax(&s_maxy, f2ord(rb.y1));
+        atomicAdd(&s_nrect, 1);
+        const float w = rb.x1 - rb.x0, hgt = rb.y1 - rb.y0;
+        sw += w; sh += hgt; swh += w * hgt;
+      } else if (rb.kind == 2) {
+        atomicAdd(&s_ninf, 1);
       }
     }
-    bar_sync_named(1, nb);
-    if (tid == 0) {
-      float gx0 = 0.f, gy0 = 0.f, invx = 0.f, invy = 0.f, fmx = -1.f, fmy = -1.f;
-      if (hdr->n_rect > 0) {
-        gx0 = ord2f(hdr->minx);
-        gy0 = ord2f(hdr->miny);
-        const float gx1 = ord2f(hdr->maxx), gy1 = ord2f(hdr->maxy);
-        const float wx = gx1 - gx0, wy = gy1 - gy0;
-        if (!isfinite(wx) || !isfinite(wy)) {
-          hdr->degenerate = 1;  // extents overflow fp32: every box is tested against every point
-        } else {
-          invx = (wx > 0.f) ? (float)G / wx : 0.f;
-          invy = (wy > 0.f) ? (float)G / wy : 0.f;
-          if (!isfinite(invx)) invx = 0.f;
-          if (!isfinite(invy)) invy = 0.f;
-          fmx = fcell(gx1, gx0, invx);
-          fmy = fcell(gy1, gy0, invy);
-        }
-      }
-      hdr->gx0 = gx0; hdr->gy0 = gy0; hdr->invx = invx; hdr->invy = invy;
-      hdr->fmaxx = fmx; hdr->fmaxy = fmy;
+    // fixed reduction tree: every slice of the frame computes bit-identical sums
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sw += __shfl_xor_sync(0xffffffffu, sw, o);
+      sh += __shfl_xor_sync(0xffffffffu, sh, o);
+      swh += __shfl_xor_sync(0xffffffffu, swh, o);
     }
-    bar_sync_named(1, nb);
-    // insertion: a half warp per box, lanes tile the box's cell range 4 x 4 at a time
-    const float gx0 = hdr->gx0, gy0 = hdr->gy0, invx = hdr->invx, invy = hdr->invy;
-    const int degenerate = hdr->degenerate;
-    const float gm1 = (float)(G - 1);
-    const int sub = lane >> 4, xx = lane & 3, yy = (lane >> 2) & 3;
-    for (int t = warp * 2 + sub; t < T; t += build_warps * 2) {
-      float x0, x1, y0, y1;
-      int kind = approx_rect(boxes + (long long)t * 7, x0, x1, y0, y1);
-      if (kind == 0) continue;
-      if (degenerate) kind = 2;
-      int cx0 = 0, cx1 = G - 1, cy0 = 0, cy1 = G - 1;
-      if (kind == 1) {
-        cx0 = (int)fminf(fcell(x0, gx0, invx), gm1); cx1 = (int)fminf(fcell(x1, gx0, invx), gm1);
-        cy0 = (int)fminf(fcell(y0, gy0, invy), gm1); cy1 = (int)fminf(fcell(y1, gy0, invy), gm1);
+    if (lane == 0) { s_sw[warp] = sw; s_sh[warp] = sh; s_swh[warp] = swh; }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    FrameHdr h;
+    h.n_rect = s_nrect; h.n_inf = s_ninf; h.pad = 0;
+    float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f, wx = 0.f, wy = 0.f;
+    bool degenerate = true;  // no finite footprint, or extents overflow fp32: one inner cell
+    if (s_nrect > 0) {
+      gx0 = ord2f(s_minx); gy0 = ord2f(s_miny);
+      gx1 = ord2f(s_maxx); gy1 = ord2f(s_maxy);
+      wx = gx1 - gx0;
+      wy = gy1 - gy0;
+      degenerate = !isfinite(wx) || !isfinite(wy);
+    }
+    int G = 1;
+    if (!degenerate) {
+      float sw = 0.f, sh = 0.f, swh = 0.f;
+      for (int w = 0; w < kNW; ++w) { sw += s_sw[w]; sh += s_sh[w]; swh += s_swh[w]; }
+      // entries(G) ~ sum over boxes of (w G / Lx + 2)(h G / Ly + 2), + (G + 2)^2 per unbounded box
+      const float ax = wx > 0.f ? sw / wx : (float)s_nrect, ay = wy > 0.f ? sh / wy : (float)s_nrect;
+      const float axy = (wx > 0.f && wy > 0.f) ? swh / (wx * wy) : (float)s_nrect;
+      const float budget = 0.75f * (float)p.L.cap;
+      G = p.L.Gmax;
+      while (G > 1) {
+        const float g = (float)G;
+        const float e = axy * g * g + 2.f * (ax + ay) * g + 4.f * (float)s_nrect +
+                        (float)s_ninf * (g + 2.f) * (g + 2.f);
+        const int rps = (G + 2 + S - 1) / S;
+        if (e <= budget && rps * (G + 2) <= kMaxSliceCells) break;  // (NaN e: keep shrinking)
+        G = G * 7 / 8;
+        if (G < 1) G = 1;
       }
-      const uint32_t bit = 1u << (t & 31);
-      const int wi = t >> 5, g8 = t >> 8;
-      const uint32_t sbit = 1u << (wi & 7);
-      for (int ty = cy0 + yy; ty <= cy1; ty += 4) {
+    } else {
+      gx0 = gy0 = gx1 = gy1 = wx = wy = 0.f;
+    }
+    h.G = G;
+    h.gx0 = gx0; h.gy0 = gy0;
+    float invx = 0.f, invy = 0.f, cwx = INFINITY, cwy = INFINITY;
+    if (!degenerate) {
+      invx = (wx > 0.f) ? (float)G / wx : 0.f;
+      invy = (wy > 0.f) ? (float)G / wy : 0.f;
+      if (!isfinite(invx)) invx = 0.f;
+      if (!isfinite(invy)) invy = 0.f;
+      if (invx > 0.f) cwx = wx / (float)G;
+      if (invy > 0.f) cwy = wy / (float)G;
+    }
+    h.invx = invx; h.invy = invy; h.cwx = cwx; h.cwy = cwy;
+    h.slopx = (fabsf(gx0) + fabsf(gx1)) * 3.814697265625e-6f;  // 2^-18
+    h.slopy = (fabsf(gy0) + fabsf(gy1)) * 3.814697265625e-6f;
+    s_hdr = h;
+  }
+  __syncthreads();
+  const FrameHdr h = s_hdr;
+  const int G = h.G, Gp = G + 2;
+  const int rps = (Gp + S - 1) / S;
+  const int row0 = min(Gp, slice * rps), row1 = min(Gp, row0 + rps);
+  const int ncell = (row1 - row0) * Gp;  // cells of this slice
+  if (slice == 0 && tid == 0) reinterpret_cast<FrameHdr*>(ws + p.L.hdr)[f] = h;
+
+  // ---- pass C: boxes touching this slice --------------------------------------------------
+  for (int i = tid; i < ncell; i += kPrepThreads) { cf[i] = 0u; word[i] = 0u; }
+  for (int t = tid; t < T; t += kPrepThreads) {
+    const RasterBox rb = get_box(t);
+    if (rb.kind == 0) continue;
+    int cx0, cx1, cy0, cy1;
+    cell_range(rb, h, cx0, cx1, cy0, cy1);
+    if (cy1 >= row0 && cy0 < row1) mine[atomicAdd(&s_nmine, 1)] = (uint16_t)t;
+  }
+  __syncthreads();
+  const int nmine = s_nmine;
+
+  // Visits every (box, local cell) incidence of this slice; a half warp per box, its 16
+  // lanes tile the box's cell range 4 x 4 at a time.  Border cells take every box whose
+  // range reaches them; inner cells are refined by the separating-axis test.
+  auto raster = [&](auto visit) {
+    const int hw = tid >> 4, l16 = tid & 15, xx = l16 & 3, yy = l16 >> 2;
+    for (int i = hw; i < nmine; i += kPrepThreads / 16) {
+      const int t = mine[i];
+      const RasterBox rb = get_box(t);
+      int cx0, cx1, cy0, cy1;
+      cell_range(rb, h, cx0, cx1, cy0, cy1);
+      const int y0 = max(cy0, row0), y1 = min(cy1, row1 - 1);
+      for (int ty = y0 + yy; ty <= y1; ty += 4)
         for (int tx = cx0 + xx; tx <= cx1; tx += 4) {
-          const int c = ty * G + tx;
-          atomicOr(table + c * Wp + wi, bit);
-          const int e = c * groups8 + g8;
-          atomicOr(summ32 + (e >> 2), sbit << (8 * (e & 3)));
+          const bool border = (tx == 0) | (tx == G + 1) | (ty == 0) | (ty == G + 1);
+          if (border || rb.kind == 2 || sat_overlap(rb, h, tx, ty)) visit(t, (ty - row0) * Gp + tx);
         }
-      }
-      if (kind == 2 && (lane & 15) == 0) {  // also a candidate for points outside the grid
-        const int c = G * G;
-        atomicOr(table + c * Wp + wi, bit);
-        const int e = c * groups8 + g8;
-        atomicOr(summ32 + (e >> 2), sbit << (8 * (e & 3)));
+    }
+  };
+
+  // ---- count pass -------------------------------------------------------------------------
+  raster([&](int, int c) { atomicAdd(&cf[c], 1u); });
+  __syncthreads();
+
+  // ---- scan: list space of the cells with >= 2 candidates ----------------------------------
+  const int cpt = (ncell + kPrepThreads - 1) / kPrepThreads;
+  const int c0 = min(ncell, tid * cpt), c1 = min(ncell, c0 + cpt);
+  uint32_t need = 0;
+  for (int c = c0; c < c1; ++c) {
+    const uint32_t n = cf[c];
+    if (n >= 2u) need += n + (n >= kCntLong ? 1u : 0u);
+  }
+  uint32_t incl = need;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp_tot[warp] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t run = 0;
+    for (int w = 0; w < kNW; ++w) {
+      const uint32_t v = s_warp_tot[w];
+      s_warp_tot[w] = run;
+      run += v;
+    }
+    uint32_t base = 0;
+    if (run > 0) {
+      base = atomicAdd(ids_used, run);
+      if ((unsigned long long)base + run > (unsigned long long)p.L.cap) s_overflow = 1;
+    }
+    s_base = base;
+  }
+  __syncthreads();
+  {
+    const bool overflow = s_overflow != 0;
+    uint32_t off = s_base + s_warp_tot[warp] + (incl - need);
+    for (int c = c0; c < c1; ++c) {
+      const uint32_t n = cf[c];
+      if (n >= 2u) {
+        if (overflow) {
+          word[c] = kCellAll;
+        } else {
+          const bool lng = n >= kCntLong;
+          word[c] = ((lng ? kCntLong : n) << kCntShift) | off;
+          if (lng) ids[off] = (uint16_t)n;
+          off += n + (lng ? 1u : 0u);
+        }
       }
     }
   }
   __syncthreads();
+
+  // ---- fill pass ----------------------------------------------------------------------------
+  {
+    const bool overflow = s_overflow != 0;
+    raster([&](int t, int c) {
+      const uint32_t old = atomicAdd(&cf[c], 0x10000u);
+      const uint32_t n = old & 0xffffu, k = old >> 16;
+      if (n == 1u) {
+        word[c] = (1u << kCntShift) | (uint32_t)t;
+      } else if (!overflow) {
+        const uint32_t w = word[c];
+        const uint32_t pos = (w & kPayMask) + ((w >> kCntShift) == kCntLong ? 1u : 0u) + k;
+        ids[pos] = (uint16_t)t;
+      }
+    });
+  }
+  __syncthreads();
+  for (int c = tid; c < ncell; c += kPrepThreads) grid[row0 * Gp + c] = word[c];
 }
 
-__device__ __forceinline__ int cell_of(float x, float y, const GridHdr& h, int G) {
-  const float fx = fcell(x, h.gx0, h.invx), fy = fcell(y, h.gy0, h.invy);
-  const bool in = (fx >= 0.f) & (fx <= h.fmaxx) & (fy >= 0.f) & (fy <= h.fmaxy);
-  const float gm1 = (float)(G - 1);
-  const int cx = (int)fminf(fx, gm1), cy = (int)fminf(fy, gm1);
-  return in ? cy * G + cx : G * G;  // cell G*G: outside every finite rectangle
+// ------------------------------------------------------------------------------------------
+// stream kernel
+// ------------------------------------------------------------------------------------------
+struct StreamParams {
+  const float* points;
+  void* out;
+  unsigned char* ws;
+  WsLayout L;
+  int pts_stride, num_points, num_boxes, num_frames;
+  int row_words;          // W
+  int batch_pts;          // P: points per warp batch (32, or 1024 / W when W > 32)
+  int batches_per_frame;  // ceil(N / P)
+  int R, tb_base, tb_rem; // ranges of the frame-major batch list: range r has tb_base + (r < tb_rem) batches
+  int slots;              // warps per range
+  int vec4;
+};
+
+// Index data is written by the prep kernel of the same PDL chain: plain (coherent, L1-cached)
+// loads, never the non-coherent read-only path.
+__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.ca.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_u16(const uint16_t* p) {
+  uint16_t v;
+  asm volatile("ld.global.ca.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return (uint32_t)v;
+}
+__device__ __forceinline__ float4 ld_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.ca.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
 }
 
-// Walks the candidate bits of one 8-word group of a cell row, one candidate per loop
-// iteration (the word switch is folded into the iteration so that a warp runs
-// max-over-lanes(candidates) iterations, not sum-over-words(max-over-lanes)).
-// Ascending box order; `on_hit(j, b)` returns true to stop (first-hit search).
+struct FrameCtx {
+  float gx0, gy0, invx, invy, gp1;
+  int Gp, f;
+  const uint32_t* grid;
+};
+
+__device__ __forceinline__ FrameCtx load_frame(const StreamParams& p, int f) {
+  const float4* h = reinterpret_cast<const float4*>(p.ws + p.L.hdr + (size_t)f * sizeof(FrameHdr));
+  const float4 a = ld_f4(h);
+  const uint32_t g = ld_u32(reinterpret_cast<const uint32_t*>(h) + 8);
+  FrameCtx c;
+  c.gx0 = a.x; c.gy0 = a.y; c.invx = a.z; c.invy = a.w;
+  c.Gp = (int)g + 2;
+  c.gp1 = (float)((int)g + 1);
+  c.f = f;
+  c.grid = reinterpret_cast<const uint32_t*>(p.ws + p.L.grid) + (size_t)f * p.L.gstride;
+  return c;
+}
+
+__device__ __forceinline__ int cell_of(float x, float y, const FrameCtx& h) {
+  return pcell(y, h.gy0, h.invy, h.gp1) * h.Gp + pcell(x, h.gx0, h.invx, h.gp1);
+}
+
+constexpr int kQueue = 64;  // (point, candidate) pairs a warp batch resolves in lane-parallel passes
+
+// Per-lane fallback: runs the exact test for every candidate of the cell word, one lane per
+// point (dense scenes, long lists, pool overflow).
 template <typename F>
-__device__ __forceinline__ void walk_group(const float4* __restrict__ sbox, const uint32_t* __restrict__ row,
-                                           uint32_t nz, int box_base, float x, float y, float z, F on_hit) {
-  uint32_t m = 0;
-  int j = 0;
-  while (true) {
-    if (m == 0u) {
-      if (nz == 0u) break;
-      j = __ffs(nz) - 1;
-      nz &= nz - 1u;
-      m = row[j];
+__device__ __forceinline__ void for_each_hit(uint32_t w, const StreamParams& p, const FrameCtx& fc, float x,
+                                             float y, float z, F on_hit) {
+  if (w == 0u) return;
+  const int T = p.num_boxes;
+  const float4* prep = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)fc.f * 2 * T;
+  if (w == kCellAll) {
+#pragma unroll 1
+    for (int t = 0; t < T; ++t)
+      if (inside_box(x, y, z, ld_f4(prep + 2 * t), ld_f4(prep + 2 * t + 1))) on_hit((uint32_t)t);
+    return;
+  }
+  const uint16_t* ids = reinterpret_cast<const uint16_t*>(p.ws + p.L.ids) + (size_t)fc.f * p.L.cap;
+  uint32_t n = w >> kCntShift, base = w & kPayMask, t;
+  if (n == 1u) {
+    t = base;
+  } else {
+    if (n == kCntLong) {
+      n = ld_u16(ids + base);
+      ++base;
     }
-    const int b = __ffs(m) - 1;
-    m &= m - 1u;
-    const int t = box_base + j * 32 + b;
-    if (inside_box(x, y, z, sbox[2 * t], sbox[2 * t + 1])) {
-      if (on_hit(j, b)) break;
-    }
+    t = ld_u16(ids + base);
+  }
+#pragma unroll 1
+  for (uint32_t j = 1;; ++j) {
+    if (inside_box(x, y, z, ld_f4(prep + 2 * t), ld_f4(prep + 2 * t + 1))) on_hit(t);
+    if (j >= n) break;
+    t = ld_u16(ids + base + j);
   }
 }
 
-template <int WL, int MODE>
-__global__ void __launch_bounds__(kThreads, 1) pib_kernel(const PibParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ GridHdr hdr_s;
-  const int T = p.num_boxes, G = p.G, Wp = p.row_words;
-  const SmemLayout lay = smem_layout(T, G, Wp, MODE == kModeBits && WL == 8);
-  float4* sbox = reinterpret_cast<float4*>(smem_raw);
-  uint32_t* table = reinterpret_cast<uint32_t*>(smem_raw + lay.table_off);
-  const uint8_t* summ = smem_raw + lay.summ_off;
-  const int groups8 = (Wp + 7) >> 3;
+// WS > 0: row words known at compile time (the common shapes), 0: taken from the params.
+// Each warp owns the batches slot, slot + slots, ... of its range (static: with ~5 batches
+// per warp at the training shape a dynamic scheduler costs more than it balances).
+template <int MODE, int WS>
+__global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const StreamParams p) {
+  extern __shared__ __align__(16) uint32_t smem_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int W = MODE == kModePart ? 1 : (WS > 0 ? WS : p.row_words);
+  const int P = (MODE == kModePart || WS > 0) ? 32 : p.batch_pts;
+  const int N = p.num_points, bpf = p.batches_per_frame;
+  const int stage_words = P * W;
+  uint32_t* stage = smem_all + (size_t)warp * (stage_words + kQueue + 4);
+  uint32_t* queue = stage + stage_words;
+  uint32_t* qcount = queue + kQueue;
 
-  const int f = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const long long items = (MODE == kModeBits) ? p.items_per_frame : (long long)p.num_points;
-  const int groups = (MODE == kModeBits) ? p.groups : 1;
-  const long long i0 = items * blockIdx.x / gridDim.x, i1 = items * (blockIdx.x + 1) / gridDim.x;
-  // CTA-local 32-bit indexing: item li in [0, n_local) is point pt0 + (rem0 + li) / groups
-  const uint32_t n_local = (uint32_t)(i1 - i0);
-  const long long pt0 = i0 / groups;
-  const uint32_t rem0 = (uint32_t)(i0 - pt0 * groups);
-  const int gshift = (groups & (groups - 1)) == 0 ? __ffs(groups) - 1 : -1;
-  const float* __restrict__ pts =
-      p.points + ((long long)f * p.num_points + pt0) * p.pts_stride;  // first point of this CTA
-  auto point_of = [&](uint32_t li, int& g) -> uint32_t {
-    if (groups == 1) { g = 0; return li; }
-    const uint32_t v = rem0 + li;
-    const uint32_t q = gshift >= 0 ? (v >> gshift) : v / (uint32_t)groups;
-    g = (int)(v - q * (uint32_t)groups);
-    return q;
+  const int r = blockIdx.x % p.R, slot = (int)(blockIdx.x / p.R) * kWarps + warp;
+  const int nb = p.tb_base + (r < p.tb_rem ? 1 : 0);                  // batches of this range
+  const int g0 = r * p.tb_base + min(r, p.tb_rem);                    // first batch of the range
+  int i = slot;                                                       // batch index inside the range
+  int f = 0, c = 0;                                                   // frame / batch inside the frame
+  if (i < nb) {
+    f = (g0 + i) / bpf;
+    c = (g0 + i) - f * bpf;
+  }
+  auto advance = [&](int& ff, int& cc) {
+    cc += p.slots;
+    while (cc >= bpf) { cc -= bpf; ++ff; }
   };
-  auto fetch = [&](uint32_t li, int& g, float& x, float& y, float& z) {
-    if (li < n_local) {
-      const uint32_t pl = point_of(li, g);
+  auto fetch = [&](bool live, int ff, int cc, float& fx, float& fy, float& fz) {
+    const int pt = cc * P + lane;
+    if (live && lane < P && pt < N) {
+      const size_t idx = (size_t)ff * N + pt;
       if (p.vec4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(pts) + pl);
-        x = v.x; y = v.y; z = v.z;
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(p.points) + idx);
+        fx = v.x; fy = v.y; fz = v.z;
       } else {
-        const float* q = pts + (size_t)pl * p.pts_stride;
-        x = __ldg(q); y = __ldg(q + 1); z = __ldg(q + 2);
+        const float* q = p.points + idx * p.pts_stride;
+        fx = __ldcs(q); fy = __ldcs(q + 1); fz = __ldcs(q + 2);
       }
     }
   };
+  // two batches of points in flight per warp, requested before the index is ready
+  float x = 0.f, y = 0.f, z = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
+  int f1 = f, c1 = c;
+  fetch(i < nb, f, c, x, y, z);
+  advance(f1, c1);
+  fetch(i + p.slots < nb, f1, c1, x1, y1, z1);
 
-  // software pipeline, distance 2: the points of the next two batches of this warp are in
-  // flight while the current one is tested (issued before the table build so that the
-  // first loads overlap it)
-  uint32_t lb = threadIdx.x & ~31u;
-  float x1 = 0.f, y1 = 0.f, z1 = 0.f, x2 = 0.f, y2 = 0.f, z2 = 0.f;
-  int g1 = 0, g2 = 0;
-  fetch(lb + lane, g1, x1, y1, z1);
-  fetch(lb + kThreads + lane, g2, x2, y2, z2);
+  // everything below reads what the prep kernel wrote
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (blockIdx.x == 0 && threadIdx.x < 32) {  // hand the id-pool cursors back zeroed
+    uint32_t* used = reinterpret_cast<uint32_t*>(p.ws + p.L.ids_used);
+    for (int q = lane; q < p.num_frames; q += 32) used[q] = 0u;
+  }
 
-  build_tables(p, p.boxes + (long long)f * T * 7, sbox, table,
-               reinterpret_cast<uint32_t*>(smem_raw + lay.summ_off), &hdr_s);
-  const GridHdr h = hdr_s;
+  int cur_f = -1;
+  FrameCtx fc;
+#pragma unroll 1
+  for (; i < nb; i += p.slots) {
+    if (f != cur_f) {
+      fc = load_frame(p, f);
+      cur_f = f;
+    }
+    const int pt0 = c * P;
+    const int nvalid = min(P, N - pt0);
+    const bool valid = lane < nvalid;
+    const float cx = x, cy = y, cz = z;
+    const int bf = f;
+    // rotate the pipeline and request the batch after next
+    x = x1; y = y1; z = z1;
+    f = f1; c = c1;
+    advance(f1, c1);
+    fetch(i + 2 * p.slots < nb, f1, c1, x1, y1, z1);
 
-  for (; lb < n_local; lb += kThreads) {
-    const uint32_t li = lb + lane;
-    const bool valid = li < n_local;
-    const float x = x1, y = y1, z = z1;
-    const int gcur = g1;
-    x1 = x2; y1 = y2; z1 = z2; g1 = g2;
-    fetch(li + 2 * kThreads, g2, x2, y2, z2);
-    const int cell = valid ? cell_of(x, y, h, G) : G * G;
+    const uint32_t w = valid ? ld_u32(fc.grid + cell_of(cx, cy, fc)) : 0u;
 
-    if constexpr (MODE == kModeBits) {
-      const int g = gcur;
-      uint32_t w[WL];
+    // zero the warp's stage (bits / all: the linear image of its P rows; part: min box index)
+    if constexpr (MODE == kModePart) {
+      stage[lane] = 0xffffffffu;
+    } else if constexpr (WS > 0) {
 #pragma unroll
-      for (int j = 0; j < WL; ++j) w[j] = 0u;
-      const uint32_t nzw = valid ? (uint32_t)summ[cell * groups8 + g] : 0u;
-      walk_group(sbox, table + cell * Wp + g * WL, nzw, g * WL * 32, x, y, z, [&](int j, int b) {
-#pragma unroll
-        for (int k = 0; k < WL; ++k) w[k] |= (k == j) ? (1u << b) : 0u;
-        return false;
-      });
-      uint32_t* out = reinterpret_cast<uint32_t*>(p.out) + ((long long)f * items + i0) * WL + (size_t)lb * WL;
-      if constexpr (WL == 8) {
-        // per-warp transpose through shared memory: lane l owns 32 B; store j writes the
-        // 16 B chunk 32*j + l, so each warp store instruction covers 512 contiguous bytes
-        uint4* st = reinterpret_cast<uint4*>(smem_raw + lay.stage_off) + (threadIdx.x >> 5) * 64;
-        st[2 * lane] = make_uint4(w[0], w[1], w[2], w[3]);
-        st[2 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
-        __syncwarp();
-        const uint4 v0 = st[lane], v1 = st[32 + lane];
-        if (lb + (lane >> 1) < n_local) __stcs(reinterpret_cast<uint4*>(out) + lane, v0);
-        if (lb + 16 + (lane >> 1) < n_local) __stcs(reinterpret_cast<uint4*>(out) + 32 + lane, v1);
-        __syncwarp();
-      } else if constexpr (WL == 4) {
-        if (valid) __stcs(reinterpret_cast<uint4*>(out) + lane, make_uint4(w[0], w[1], w[2], w[3]));
-      } else if constexpr (WL == 2) {
-        if (valid) __stcs(reinterpret_cast<uint2*>(out) + lane, make_uint2(w[0], w[1]));
+      for (int k = 0; k < (32 * WS) / 128; ++k) reinterpret_cast<uint4*>(stage)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+      if ((32 * WS) % 128 != 0 && lane < (32 * WS % 128) / 4)
+        reinterpret_cast<uint4*>(stage)[(32 * WS) / 128 * 32 + lane] = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll 1
+      for (int k = lane; k < (stage_words >> 2); k += 32) reinterpret_cast<uint4*>(stage)[k] = make_uint4(0, 0, 0, 0);
+    }
+    if (lane == 0) *qcount = 0u;
+    __syncwarp();
+    // reserve queue space for this lane's candidates
+    uint32_t cnt = w >> kCntShift;
+    if (cnt == kCntLong) cnt = kQueue + 1;  // long list or pool overflow: per-lane path
+    const uint32_t pos = cnt ? atomicAdd(qcount, cnt) : 0u;
+    __syncwarp();
+    const uint32_t total = *qcount;
+    auto mark = [&](uint32_t row, uint32_t t, bool own) {
+      if constexpr (MODE == kModePart) {
+        if (own) stage[row] = min(stage[row], t);
+        else atomicMin(&stage[row], t);
       } else {
-        if (valid) __stcs(out + lane, w[0]);
+        if (own) stage[row * W + (t >> 5)] |= 1u << (t & 31u);
+        else atomicOr(&stage[row * W + (t >> 5)], 1u << (t & 31u));
       }
-    } else if constexpr (MODE == kModeAll) {
-      int32_t* out = reinterpret_cast<int32_t*>(p.out) + ((long long)f * p.num_points + i0 + lb) * T;
-      const int nvalid = (int)min(32u, n_local - lb);
-      for (int g0 = 0; g0 < Wp; g0 += WL) {
-        uint32_t w[WL];
+    };
+    if (total <= kQueue) {
+      // expand (point, candidate) pairs, then test them one pair per lane
+      if (cnt == 1u) {
+        queue[pos] = ((uint32_t)lane << 16) | (w & kPayMask);
+      } else if (cnt > 1u) {
+        const uint16_t* ids = reinterpret_cast<const uint16_t*>(p.ws + p.L.ids) + (size_t)bf * p.L.cap + (w & kPayMask);
+#pragma unroll 1
+        for (uint32_t j = 0; j < cnt; ++j) queue[pos + j] = ((uint32_t)lane << 16) | ld_u16(ids + j);
+      }
+      __syncwarp();
+      const float4* prep = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)bf * 2 * p.num_boxes;
+#pragma unroll 1
+      for (uint32_t q0 = 0; q0 < total; q0 += 32) {
+        const bool have = q0 + lane < total;
+        const uint32_t e = have ? queue[q0 + lane] : 0u;
+        const uint32_t src = e >> 16, t = e & 0xffffu;
+        const float px = __shfl_sync(0xffffffffu, cx, src), py = __shfl_sync(0xffffffffu, cy, src),
+                    pz = __shfl_sync(0xffffffffu, cz, src);
+        if (have && inside_box(px, py, pz, ld_f4(prep + 2 * t), ld_f4(prep + 2 * t + 1))) mark(src, t, false);
+      }
+    } else {
+      for_each_hit(w, p, fc, cx, cy, cz, [&](uint32_t t) { mark((uint32_t)lane, t, true); });
+    }
+    __syncwarp();
+
+    if constexpr (MODE == kModePart) {
+      if (valid) __stcs(reinterpret_cast<int32_t*>(p.out) + (size_t)bf * N + pt0 + lane, (int32_t)stage[lane]);
+    } else if constexpr (MODE == kModeBits) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(p.out) + ((size_t)bf * N + pt0) * W;
+      const int nw = nvalid * W;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int n4 = nw >> 2;
+        if (WS > 0 && nvalid == 32 && (32 * WS) % 128 == 0) {
 #pragma unroll
-        for (int j = 0; j < WL; ++j) w[j] = 0u;
-        uint32_t nzw = 0u;
-        if (valid) nzw = WL == 8 ? (uint32_t)summ[cell * groups8 + (g0 >> 3)] : (uint32_t)summ[cell];
-        walk_group(sbox, table + cell * Wp + g0, nzw, g0 * 32, x, y, z, [&](int j, int b) {
-#pragma unroll
-          for (int k = 0; k < WL; ++k) w[k] |= (k == j) ? (1u << b) : 0u;
-          return false;
-        });
-        // expand: for every point of the warp, lane l writes box (g0 + j) * 32 + l
-#pragma unroll
-        for (int j = 0; j < WL; ++j) {
-          const int t = (g0 + j) * 32 + lane;
-          if ((g0 + j) * 32 < T) {
-            for (int q = 0; q < nvalid; ++q) {
-              const uint32_t word = __shfl_sync(0xffffffffu, w[j], q);
-              if (t < T) __stcs(out + (long long)q * T + t, (int32_t)((word >> lane) & 1u));
-            }
+          for (int k = 0; k < (32 * WS) / 128; ++k)
+            __stcs(reinterpret_cast<uint4*>(dst) + k * 32 + lane, reinterpret_cast<const uint4*>(stage)[k * 32 + lane]);
+        } else {
+#pragma unroll 1
+          for (int k = lane; k < n4; k += 32)
+            __stcs(reinterpret_cast<uint4*>(dst) + k, reinterpret_cast<const uint4*>(stage)[k]);
+          for (int k = (n4 << 2) + lane; k < nw; k += 32) __stcs(dst + k, stage[k]);
+        }
+      } else {
+        for (int k = lane; k < nw; k += 32) __stcs(dst + k, stage[k]);
+      }
+    } else {  // kModeAll: int32 [N, T] rows, lane l writes boxes 4l..4l+3 (+128 k)
+      const int T = p.num_boxes;
+      int32_t* dst = reinterpret_cast<int32_t*>(p.out) + ((size_t)bf * N + pt0) * T;
+      if ((T & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (int q = 0; q < nvalid; ++q) {
+          for (int t4 = lane * 4; t4 < T; t4 += 128) {
+            const uint32_t nib = stage[q * W + (t4 >> 5)] >> (t4 & 31);
+            __stcs(reinterpret_cast<int4*>(dst + (size_t)q * T + t4),
+                   make_int4(nib & 1u, (nib >> 1) & 1u, (nib >> 2) & 1u, (nib >> 3) & 1u));
           }
         }
-      }
-    } else {  // kModePart: first enclosing box, ascending
-      if (valid) {
-        int idx = -1;
-        for (int g = 0; g < groups8 && idx < 0; ++g) {
-          walk_group(sbox, table + cell * Wp + g * 8, (uint32_t)summ[cell * groups8 + g], g * 256, x, y, z,
-                     [&](int j, int b) {
-                       idx = g * 256 + j * 32 + b;
-                       return true;
-                     });
-        }
-        __stcs(reinterpret_cast<int32_t*>(p.out) + (long long)f * p.num_points + i0 + li, idx);
+      } else {
+        for (int q = 0; q < nvalid; ++q)
+          for (int t = lane; t < T; t += 32)
+            __stcs(dst + (size_t)q * T + t, (int32_t)((stage[q * W + (t >> 5)] >> (t & 31)) & 1u));
       }
     }
+    __syncwarp();
   }
 }
 
@@ -478,26 +775,32 @@ __global__ void box_prep_test_kernel(const float* __restrict__ boxes, int T, flo
   }
 }
 
-int g_tune_grid = 0, g_tune_ctas = 0;
-
-template <int WL, int MODE>
-int launch_pib(const PibParams& p, int B, int ctas_per_frame, size_t smem, cudaStream_t st) {
-  static int configured_smem[64];  // per device, grows monotonically
+template <int MODE, int WS>
+int launch_stream(const StreamParams& p, int grid, size_t smem, cudaStream_t st) {
+  static int configured[64];
   int dev = 0;
   GGA_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && (int)smem > configured_smem[dev]) {
-    GGA_CHECK_CUDA(cudaFuncSetAttribute(pib_kernel<WL, MODE>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured_smem[dev] = (int)smem;
+  if (dev >= 0 && dev < 64 && (int)smem > configured[dev] && smem > 48 * 1024) {
+    GGA_CHECK_CUDA(
+        cudaFuncSetAttribute(pib_stream_kernel<MODE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = (int)smem;
   }
-  dim3 grid(ctas_per_frame, B);
-  pib_kernel<WL, MODE><<<grid, kThreads, smem, st>>>(p);
-  GGA_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kStreamThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_kernel<MODE, WS>, p));
   return GGA_OK;
 }
 
-int run_pib(int mode, const float* points, int pts_stride, const float* boxes, void* out, int B,
-            int num_points, int num_boxes, void* stream) {
+int run_pib(int mode, const float* points, int pts_stride, const float* boxes, void* out, int B, int num_points,
+            int num_boxes, void* workspace, size_t workspace_bytes, void* stream) {
   GGA_REQUIRE(B >= 0 && num_points >= 0 && num_boxes >= 0, "negative size");
   GGA_REQUIRE(pts_stride >= 3, "pts_stride must be >= 3 (got %d)", pts_stride);
   if (B == 0 || num_points == 0) return GGA_OK;
@@ -512,51 +815,76 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   GGA_REQUIRE(points && out, "null points/out pointer");
   GGA_REQUIRE(boxes, "null boxes pointer");
   GGA_REQUIRE(B <= 65535, "at most 65535 frames per call (got %d)", B);
-
-  PibParams p;
-  p.points = points; p.boxes = boxes; p.out = out;
-  p.pts_stride = pts_stride; p.num_points = num_points; p.num_boxes = num_boxes;
-  p.row_words = gga_pib_row_words(num_boxes);
-  const int WL = p.row_words >= 8 ? 8 : p.row_words;
-  p.groups = p.row_words / WL;
-  p.items_per_frame = (long long)num_points * p.groups;
-  p.vec4 = (pts_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0) ? 1 : 0;
-
-  // shared memory: boxes + cull grid + summaries (+ transpose buffer); pick the finest grid
-  // that fits, capped by the automatic / tuned resolution
-  const size_t max_smem = (size_t)gga_max_smem_optin() - 1024;  // static smem + slack
-  const bool need_stage = (mode == kModeBits && WL == 8);
-  if (smem_layout(num_boxes, 2, p.row_words, need_stage).total > max_smem) {
-    gga_set_error("num_boxes=%d exceeds the shared-memory capacity of this build", num_boxes);
+  if (num_boxes > kMaxBoxes) {
+    gga_set_error("num_boxes=%d exceeds the %d boxes per frame this build indexes", num_boxes, kMaxBoxes);
     return GGA_ERR_UNSUPPORTED;
   }
-  int want = g_tune_grid > 0 ? g_tune_grid : 40;
-  if (want < 1) want = 1;
-  if (want > kMaxGrid) want = kMaxGrid;
-  int G = want;
-  while (G > 2 && smem_layout(num_boxes, G, p.row_words, need_stage).total > max_smem) --G;
-  p.G = G;
-  const size_t smem = smem_layout(num_boxes, G, p.row_words, need_stage).total;
+  const int Gmax = pick_gmax(num_points, num_boxes);
+  const WsLayout L = ws_layout(B, num_boxes, Gmax);
+  GGA_REQUIRE(workspace != nullptr, "null workspace (size it with gga_pib_workspace_bytes, zero it once)");
+  GGA_REQUIRE(workspace_bytes >= L.total, "workspace too small: %zu bytes given, %zu needed", workspace_bytes,
+              L.total);
+  GGA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, "workspace must be 256-byte aligned");
 
-  int ctas = g_tune_ctas > 0 ? g_tune_ctas : gga_sm_count() / B;
-  if (ctas < 1) ctas = 1;
-  const long long items = (mode == kModeBits) ? p.items_per_frame : (long long)num_points;
-  const long long max_ctas = (items + kThreads - 1) / kThreads;
-  if (ctas > max_ctas) ctas = (int)max_ctas;
+  const int nsm = gga_sm_count();
+  const int occ = g_tune_occ > 0 ? (g_tune_occ > kOcc ? kOcc : g_tune_occ) : kOcc;
 
-#define GGA_DISPATCH(WLV)                                                                  \
-  do {                                                                                     \
-    if (mode == kModeBits) return launch_pib<WLV, kModeBits>(p, B, ctas, smem, st);        \
-    if (mode == kModeAll) return launch_pib<WLV, kModeAll>(p, B, ctas, smem, st);          \
-    return launch_pib<WLV, kModePart>(p, B, ctas, smem, st);                               \
-  } while (0)
-  switch (WL) {
-    case 1: GGA_DISPATCH(1);
-    case 2: GGA_DISPATCH(2);
-    case 4: GGA_DISPATCH(4);
-    default: GGA_DISPATCH(8);
+  StreamParams sp;
+  sp.points = points; sp.out = out; sp.ws = static_cast<unsigned char*>(workspace); sp.L = L;
+  sp.pts_stride = pts_stride; sp.num_points = num_points; sp.num_boxes = num_boxes; sp.num_frames = B;
+  sp.row_words = gga_pib_row_words(num_boxes);
+  sp.batch_pts = sp.row_words <= 32 ? 32 : (1024 / sp.row_words < 1 ? 1 : 1024 / sp.row_words);
+  if (mode == kModePart) sp.batch_pts = 32;
+  sp.batches_per_frame = (num_points + sp.batch_pts - 1) / sp.batch_pts;
+  const long long tb = (long long)sp.batches_per_frame * B;
+  GGA_REQUIRE(tb < (1ll << 30), "too many point batches in one call");
+  sp.slots = occ * kWarps;
+  long long R = (tb + sp.slots - 1) / sp.slots;
+  if (R > nsm) R = nsm;
+  if (R < 1) R = 1;
+  sp.R = (int)R;
+  sp.tb_base = (int)(tb / R);
+  sp.tb_rem = (int)(tb % R);
+  sp.vec4 = (pts_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0) ? 1 : 0;
+  const int grid = (int)R * occ;
+  const int stage_words = mode == kModePart ? 32 : sp.row_words * sp.batch_pts;
+  const size_t smem = (size_t)(stage_words + kQueue + 4) * 4 * kWarps;
+  GGA_REQUIRE(smem <= 200 * 1024, "row too wide for the stage");
+
+  // prep: S slices per frame
+  int S = nsm / B;
+  if (S < 1) S = 1;
+  if (S > Gmax + 2) S = Gmax + 2;
+  {
+    const int gp = Gmax + 2;
+    const int min_s = (gp * gp + kMaxSliceCells - 1) / kMaxSliceCells + 1;  // keeps Gmax reachable
+    if (S < min_s && (long long)B * min_s <= 4ll * nsm) S = min_s;
   }
-#undef GGA_DISPATCH
+  PrepParams pp;
+  pp.boxes = boxes; pp.ws = sp.ws; pp.L = L; pp.T = num_boxes;
+  pp.ncache = num_boxes < 2048 ? num_boxes : 2048;
+  const size_t prep_smem = (size_t)2 * (kMaxSliceCells + 4) * 4 + align_up((size_t)num_boxes * 2, 16) +
+                           (size_t)pp.ncache * kBoxWords * 4;
+  {
+    static int configured[64];
+    int dev = 0;
+    GGA_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && (int)prep_smem > configured[dev] && prep_smem > 48 * 1024) {
+      GGA_CHECK_CUDA(
+          cudaFuncSetAttribute(pib_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+      configured[dev] = (int)prep_smem;
+    }
+  }
+  pib_prep_kernel<<<dim3(S, B), kPrepThreads, prep_smem, st>>>(pp);
+  GGA_CHECK_CUDA(cudaGetLastError());
+
+  if (mode == kModeBits) {
+    if (sp.row_words == 8) return launch_stream<kModeBits, 8>(sp, grid, smem, st);
+    if (sp.row_words == 2) return launch_stream<kModeBits, 2>(sp, grid, smem, st);
+    return launch_stream<kModeBits, 0>(sp, grid, smem, st);
+  }
+  if (mode == kModeAll) return launch_stream<kModeAll, 0>(sp, grid, smem, st);
+  return launch_stream<kModePart, 0>(sp, grid, smem, st);
 }
 
 }  // namespace
@@ -569,28 +897,44 @@ extern "C" int gga_pib_row_words(int num_boxes) {
   return 8 * ((num_boxes + 255) / 256);
 }
 
-extern "C" int gga_pib_set_tuning(int grid_cells, int ctas_per_frame) {
+extern "C" int gga_pib_set_tuning(int grid_cells, int ctas_per_sm) {
   g_tune_grid = grid_cells;
-  g_tune_ctas = ctas_per_frame;
+  g_tune_occ = ctas_per_sm;
   return GGA_OK;
 }
 
-extern "C" int gga_points_in_boxes_bits(const float* points, int pts_stride, const float* boxes,
-                                        uint32_t* bits, int B, int num_points, int num_boxes,
-                                        void* stream) {
-  return run_pib(kModeBits, points, pts_stride, boxes, bits, B, num_points, num_boxes, stream);
+extern "C" size_t gga_pib_workspace_bytes(int B, int num_points, int num_boxes) {
+  if (B <= 0 || num_points <= 0 || num_boxes <= 0) return 256;
+  if (num_boxes > kMaxBoxes) num_boxes = kMaxBoxes;
+  return ws_layout(B, num_boxes, pick_gmax(num_points, num_boxes)).total;
 }
 
-extern "C" int gga_points_in_boxes_all(const float* points, int pts_stride, const float* boxes,
-                                       int32_t* out, int B, int num_points, int num_boxes,
-                                       void* stream) {
-  return run_pib(kModeAll, points, pts_stride, boxes, out, B, num_points, num_boxes, stream);
+extern "C" int gga_pib_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  GGA_REQUIRE(workspace != nullptr || workspace_bytes == 0, "null workspace");
+  if (workspace_bytes == 0) return GGA_OK;
+  GGA_CHECK_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, gga_stream(stream)));
+  return GGA_OK;
 }
 
-extern "C" int gga_points_in_boxes_part(const float* points, int pts_stride, const float* boxes,
-                                        int32_t* out, int B, int num_points, int num_boxes,
-                                        void* stream) {
-  return run_pib(kModePart, points, pts_stride, boxes, out, B, num_points, num_boxes, stream);
+extern "C" int gga_points_in_boxes_bits(const float* points, int pts_stride, const float* boxes, uint32_t* bits,
+                                        int B, int num_points, int num_boxes, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return run_pib(kModeBits, points, pts_stride, boxes, bits, B, num_points, num_boxes, workspace,
+                 workspace_bytes, stream);
+}
+
+extern "C" int gga_points_in_boxes_all(const float* points, int pts_stride, const float* boxes, int32_t* out,
+                                       int B, int num_points, int num_boxes, void* workspace,
+                                       size_t workspace_bytes, void* stream) {
+  return run_pib(kModeAll, points, pts_stride, boxes, out, B, num_points, num_boxes, workspace, workspace_bytes,
+                 stream);
+}
+
+extern "C" int gga_points_in_boxes_part(const float* points, int pts_stride, const float* boxes, int32_t* out,
+                                        int B, int num_points, int num_boxes, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  return run_pib(kModePart, points, pts_stride, boxes, out, B, num_points, num_boxes, workspace,
+                 workspace_bytes, stream);
 }
 
 extern "C" int gga_points_in_boxes_all_host(const float* points, int pts_stride, const float* boxes,
@@ -601,23 +945,28 @@ extern "C" int gga_points_in_boxes_all_host(const float* points, int pts_stride,
   const size_t pb = (size_t)B * num_points * pts_stride * sizeof(float);
   const size_t bb = (size_t)B * num_boxes * 7 * sizeof(float);
   const size_t ob = (size_t)B * num_points * num_boxes * sizeof(int32_t);
+  const size_t wb = gga_pib_workspace_bytes(B, num_points, num_boxes);
   float *dp = nullptr, *db = nullptr;
   int32_t* dout = nullptr;
+  void* dws = nullptr;
   cudaStream_t st;
   GGA_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   int rc = GGA_OK;
   cudaError_t e = cudaMallocAsync(&dp, pb, st);
   if (e == cudaSuccess) e = cudaMallocAsync(&db, bb, st);
   if (e == cudaSuccess) e = cudaMallocAsync(&dout, ob, st);
+  if (e == cudaSuccess) e = cudaMallocAsync(&dws, wb, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(dws, 0, wb, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(dp, points, pb, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(db, boxes, bb, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    rc = run_pib(kModeAll, dp, pts_stride, db, dout, B, num_points, num_boxes, st);
+    rc = run_pib(kModeAll, dp, pts_stride, db, dout, B, num_points, num_boxes, dws, wb, st);
     if (rc == GGA_OK) e = cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, st);
   }
   if (dp) cudaFreeAsync(dp, st);
   if (db) cudaFreeAsync(db, st);
   if (dout) cudaFreeAsync(dout, st);
+  if (dws) cudaFreeAsync(dws, st);
   const cudaError_t e2 = cudaStreamSynchronize(st);
   cudaStreamDestroy(st);
   if (rc != GGA_OK) return rc;

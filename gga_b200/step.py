@@ -43,11 +43,14 @@ class GeometryStep:
         self.loss = torch.empty((n, 4 if self.kind == _lib.LOSS_L1 else 1), dtype=torch.float32, device=dev)
         self.loss_sum = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.grad_boxes = torch.empty((n, 7), dtype=torch.float32, device=dev)
+        self.ws = torch.zeros((int(L.gga_pib_workspace_bytes(self.F, self.N, self.M)),), dtype=torch.uint8,
+                              device=dev)
+        self.side = torch.cuda.Stream(device=dev)   # the box kernel runs beside the membership kernels
         self.graph = None
         self._host = None
 
     # ------------------------------------------------------------------ device-resident step
-    def run(self, points, boxes, lidar2img, target, weight=None, avg_factor=None, stream=None):
+    def run(self, points, boxes, lidar2img, target, weight=None, avg_factor=None):
         """points [F,N,pts_stride], boxes [F,M,7], lidar2img [F,M,4,4] (one calib per object,
         the GGA_lidar2img layout) or [4,4], target [F,M,4], weight [F,M] — contiguous fp32 CUDA
         tensors.  Enqueues the step on the current stream; returns nothing (results are in
@@ -55,9 +58,14 @@ class GeometryStep:
         gradients are already scaled by ``loss_weight / avg_factor``)."""
         L = self.L
         n = self.F * self.M
-        st = _lib.current_stream(self.device) if stream is None else stream
+        cur = torch.cuda.current_stream(self.device)
+        st = cur.cuda_stream
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        self.side.wait_event(fork)
         _lib.check(L.gga_points_in_boxes_bits(points.data_ptr(), self.pts_stride, boxes.data_ptr(),
-                                              self.bits.data_ptr(), self.F, self.N, self.M, st),
+                                              self.bits.data_ptr(), self.F, self.N, self.M,
+                                              self.ws.data_ptr(), self.ws.numel(), st),
                    'points_in_boxes_bits')
         a = _lib.BoxLossArgs()
         a.boxes = boxes.data_ptr()
@@ -71,7 +79,10 @@ class GeometryStep:
         a.grad_scale = self.loss_weight / float(avg_factor if avg_factor is not None else max(n, 1))
         a.box2d, a.loss, a.loss_sum = self.box2d.data_ptr(), self.loss.data_ptr(), self.loss_sum.data_ptr()
         a.grad_boxes = self.grad_boxes.data_ptr()
-        _lib.check(L.gga_box_project_loss(a, st), 'box_project_loss')
+        _lib.check(L.gga_box_project_loss(a, self.side.cuda_stream), 'box_project_loss')
+        join = torch.cuda.Event()
+        join.record(self.side)
+        cur.wait_event(join)
 
     def capture(self, *args, **kw):
         """Warm up, then capture ``run(*args)`` into a CUDA graph (inputs are baked in by address)."""

@@ -50,27 +50,42 @@ int gga_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_m
  * Box t of a point is bit (t & 31) of word (t >> 5); padding bits are zero. */
 int gga_pib_row_words(int num_boxes);
 
+/* Scratch memory of one membership call (the per-frame box index built on the device:
+ * contract terms of every box, BEV cell grid, candidate id lists, tile counters).
+ * The caller owns it, like every other buffer: device memory, 256-byte aligned, at least
+ * gga_pib_workspace_bytes(B, num_points, num_boxes) bytes, zero-filled ONCE after allocation
+ * (gga_pib_workspace_init, or any memset); calls leave it ready for the next call.  A
+ * workspace must not be shared by calls that can run concurrently (different streams). */
+size_t gga_pib_workspace_bytes(int B, int num_points, int num_boxes);
+int gga_pib_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+
 /* bits : uint32 [B, num_points, gga_pib_row_words(num_boxes)] */
 int gga_points_in_boxes_bits(const float* points, int pts_stride, const float* boxes,
-                             uint32_t* bits, int B, int num_points, int num_boxes, void* stream);
+                             uint32_t* bits, int B, int num_points, int num_boxes,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* out : int32 [B, num_points, num_boxes], 0/1 — exact layout of mmcv points_in_boxes_all.
  * Every element is written (no pre-zeroing needed). */
 int gga_points_in_boxes_all(const float* points, int pts_stride, const float* boxes, int32_t* out,
-                            int B, int num_points, int num_boxes, void* stream);
+                            int B, int num_points, int num_boxes, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* out : int32 [B, num_points], index of the first enclosing box or -1 — mmcv
  * points_in_boxes_part. */
 int gga_points_in_boxes_part(const float* points, int pts_stride, const float* boxes,
-                             int32_t* out, int B, int num_points, int num_boxes, void* stream);
+                             int32_t* out, int B, int num_points, int num_boxes, void* workspace,
+                             size_t workspace_bytes, void* stream);
 
 /* HOST buffers in and out (the points_in_boxes_cpu signature: CPU tensors), computed on
- * the current device: H2D, kernel, D2H, synchronous.  out : int32 [B, num_points, num_boxes]. */
+ * the current device: H2D, kernels, D2H, synchronous; scratch is allocated internally.
+ * out : int32 [B, num_points, num_boxes]. */
 int gga_points_in_boxes_all_host(const float* points, int pts_stride, const float* boxes,
                                  int32_t* out, int B, int num_points, int num_boxes);
 
-/* Tuning knobs (0 = automatic): BEV cull-grid cells per side, CTAs per frame. */
-int gga_pib_set_tuning(int grid_cells, int ctas_per_frame);
+/* Tuning knobs (0 = automatic): BEV index cells per side (upper bound; the device picks the
+ * per-frame resolution), resident CTAs per SM of the streaming kernel.  Changing the first
+ * changes gga_pib_workspace_bytes. */
+int gga_pib_set_tuning(int grid_cells, int ctas_per_sm);
 
 /* ------------------------------------------------------------------------------------
  * Part 2 + 3 — box corners -> projection -> 8-corner min/max -> (clamped) 2D box, and the

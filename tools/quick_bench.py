@@ -56,7 +56,9 @@ def main():
                 p, b = pool[it[0] % a.pool]
                 o = outs[it[0] % a.pool]
                 it[0] += 1
-                rc = L.gga_points_in_boxes_bits(p.data_ptr(), 4, b.data_ptr(), o.data_ptr(), a.frames, N, M, st)
+                ws = G.ops.workspace(p.device, a.frames, N, M)
+                rc = L.gga_points_in_boxes_bits(p.data_ptr(), 4, b.data_ptr(), o.data_ptr(), a.frames, N, M,
+                                                ws.data_ptr(), ws.numel(), st)
                 assert rc == 0
             ms = time_ms(fn)
             r = dict(cfg=a.cfg, grid=g, ctas=ct, ms=round(ms, 4), gbs=round(bytes_step / ms / 1e6, 1),
