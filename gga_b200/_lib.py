@@ -56,6 +56,8 @@ SIGNATURES = {
     'gga_match_dt_gt': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p], c_int),
     'gga_image_box_overlap_f64': ([c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
+    'gga_test_pib_phase': ([c_int], c_int),
+    'gga_test_pib_trace': ([c_void_p], c_int),
     'gga_test_sincos': ([c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p], c_int),
     'gga_test_box_prep': ([c_void_p, c_int, c_void_p, c_void_p], c_int),
 }

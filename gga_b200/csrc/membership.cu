@@ -34,14 +34,24 @@ namespace {
 constexpr int kStreamThreads = 256;
 constexpr int kWarps = kStreamThreads / 32;
 constexpr int kOcc = 5;  // stream CTAs per SM (48 registers per thread)
-constexpr int kPrepThreads = 256;
+constexpr int kPrepThreads = 512;
+constexpr int kMaxRanges = 1024;
 constexpr int kMaxSliceCells = 4096;
 constexpr int kMaxG = 256;
-constexpr uint32_t kCntShift = 22;
-constexpr uint32_t kPayMask = (1u << kCntShift) - 1u;
-constexpr uint32_t kCntLong = 1023u;        // count field value meaning "real count is ids[payload]"
-constexpr uint32_t kCellAll = 0xffffffffu;  // every box is a candidate (pool overflow fallback)
-constexpr uint32_t kMaxCap = kPayMask - 1u;
+// Cell word of the frame index (32 bits):
+//   0                      empty
+//   01 | 0 | id0           one candidate            (ids are 15 bits)
+//   10 | id1 | id0         two candidates
+//   11 | cnt:10 | off:20   list of cnt ids at ids[off]; cnt == 1023: real count is ids[off], list at off + 1
+//   0xffffffff             every box is a candidate (id pool overflow fallback)
+constexpr uint32_t kKindShift = 30;
+constexpr uint32_t kIdMask = 0x7fffu;
+constexpr uint32_t kListCntShift = 20;
+constexpr uint32_t kListOffMask = (1u << kListCntShift) - 1u;
+constexpr uint32_t kCntLong = 1023u;
+constexpr uint32_t kCellAll = 0xffffffffu;
+constexpr uint32_t kMaxCap = kListOffMask - 1u;
+constexpr int kInline = 4;  // candidates a cell can hold in shared memory during the single raster pass
 constexpr int kMaxBoxes = 32767;
 
 enum { kModeBits = 0, kModeAll = 1, kModePart = 2 };
@@ -190,7 +200,8 @@ inline WsLayout ws_layout(int F, int T, int Gmax) {
   return L;
 }
 
-int g_tune_grid = 0, g_tune_occ = 0;
+int g_tune_grid = 0, g_tune_occ = 0, g_tune_dynamic = 0, g_tune_phase = 0;
+unsigned long long* g_trace = nullptr;
 
 inline int pick_gmax(int N, int T) {
   if (g_tune_grid > 0) return g_tune_grid > kMaxG ? kMaxG : g_tune_grid;
@@ -213,19 +224,6 @@ struct PrepParams {
   int ncache;  // boxes whose raster terms are cached in shared memory
 };
 
-// Conservative "could a point of the INNER cell (tx, ty) (padded coordinates 1..G) pass the
-// exact test of this box": separating-axis test in the box frame.
-__device__ __forceinline__ bool sat_overlap(const RasterBox& rb, const FrameHdr& h, int tx, int ty) {
-  const float ccx = h.gx0 + ((float)tx - 0.5f) * h.cwx, ccy = h.gy0 + ((float)ty - 0.5f) * h.cwy;
-  const float dx = ccx - rb.cx, dy = ccy - rb.cy;
-  const float lx = dx * rb.cs - dy * rb.sn, ly = dx * rb.sn + dy * rb.cs;
-  const float Hx = 0.5f * h.cwx + h.slopx, Hy = 0.5f * h.cwy + h.slopy;
-  const float ac = fabsf(rb.cs), as = fabsf(rb.sn);
-  const float infl = (rb.hx + rb.hy + Hx + Hy) * 1.220703125e-4f;
-  const float bx = rb.hx + ac * Hx + as * Hy + infl, by = rb.hy + as * Hx + ac * Hy + infl;
-  return !(fabsf(lx) > bx) && !(fabsf(ly) > by);  // NaN / inf anywhere -> keep the box
-}
-
 __device__ __forceinline__ void cell_range(const RasterBox& rb, const FrameHdr& h, int& cx0, int& cx1, int& cy0,
                                            int& cy1) {
   const int G = h.G;
@@ -241,21 +239,45 @@ __device__ __forceinline__ void cell_range(const RasterBox& rb, const FrameHdr& 
 
 constexpr int kBoxWords = 11;
 
+// Per-(box, grid) constants of the separating-axis test, hoisted out of the cell loop.
+struct SatBox {
+  float cx, cy, cs, sn, bx, by;
+};
+__device__ __forceinline__ SatBox sat_box(const RasterBox& rb, const FrameHdr& h) {
+  SatBox s;
+  s.cx = rb.cx; s.cy = rb.cy; s.cs = rb.cs; s.sn = rb.sn;
+  const float Hx = 0.5f * h.cwx + h.slopx, Hy = 0.5f * h.cwy + h.slopy;
+  const float ac = fabsf(rb.cs), as = fabsf(rb.sn);
+  const float infl = (rb.hx + rb.hy + Hx + Hy) * 1.220703125e-4f;
+  s.bx = rb.hx + ac * Hx + as * Hy + infl;
+  s.by = rb.hy + as * Hx + ac * Hy + infl;
+  return s;
+}
+// Conservative "could a point of the INNER cell (tx, ty) (padded coordinates 1..G) pass the
+// exact test of this box": separating-axis test in the box frame.
+__device__ __forceinline__ bool sat_overlap(const SatBox& s, const FrameHdr& h, int tx, int ty) {
+  const float dx = h.gx0 + ((float)tx - 0.5f) * h.cwx - s.cx, dy = h.gy0 + ((float)ty - 0.5f) * h.cwy - s.cy;
+  const float lx = dx * s.cs - dy * s.sn, ly = dx * s.sn + dy * s.cs;
+  return !(fabsf(lx) > s.bx) && !(fabsf(ly) > s.by);  // NaN / inf anywhere -> keep the box
+}
+
 __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams p) {
   // let the dependent stream kernel start its prologue right away
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) unsigned char dsm[];
-  uint32_t* cf = reinterpret_cast<uint32_t*>(dsm);                            // count | fill << 16
-  uint32_t* word = cf + (kMaxSliceCells + 4);                                 // offsets, then cell words
-  uint16_t* mine = reinterpret_cast<uint16_t*>(word + (kMaxSliceCells + 4));  // [T] boxes touching this slice
-  float* cbox = reinterpret_cast<float*>(dsm + (size_t)2 * (kMaxSliceCells + 4) * 4 + align_up((size_t)p.T * 2, 16));
+  constexpr int kCells = kMaxSliceCells + 4;
+  uint32_t* cf = reinterpret_cast<uint32_t*>(dsm);   // candidates per cell (count pass), then fill cursor << 16
+  uint32_t* word = cf + kCells;                      // inline ids 0,1 -> final cell word
+  uint32_t* word2 = word + kCells;                   // inline ids 2,3 -> list offset
+  uint16_t* mine = reinterpret_cast<uint16_t*>(word2 + kCells);  // [T] boxes touching this slice
+  float* cbox = reinterpret_cast<float*>(dsm + (size_t)3 * kCells * 4 + align_up((size_t)p.T * 2, 16));
+  constexpr int kNW = kPrepThreads / 32;
   __shared__ uint32_t s_minx, s_miny, s_maxx, s_maxy;
   __shared__ int s_nrect, s_ninf, s_nmine, s_overflow;
-  __shared__ float s_sw[kPrepThreads / 32], s_sh[kPrepThreads / 32], s_swh[kPrepThreads / 32];
+  __shared__ float s_sw[kNW], s_sh[kNW], s_swh[kNW];
   __shared__ FrameHdr s_hdr;
-  __shared__ uint32_t s_base, s_warp_tot[kPrepThreads / 32];
+  __shared__ uint32_t s_base, s_warp_tot[kNW];
 
-  constexpr int kNW = kPrepThreads / 32;
   const int T = p.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int f = blockIdx.y, slice = blockIdx.x, S = gridDim.x;
   const float* __restrict__ boxes = p.boxes + (size_t)f * T * 7;
@@ -285,8 +307,9 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
   }
   __syncthreads();
 
-  // ---- pass A (warps 0..6): footprints, their extent, and the sums that predict the list
-  //      length; warp 7 meanwhile evaluates the exact contract terms of this slice's boxes ----
+  // ---- pass A (all warps but the last): footprints, their extent, and the sums that predict
+  //      the list length; the last warp meanwhile evaluates the exact contract terms of this
+  //      slice's share of the boxes ------------------------------------------------------------
   if (warp == kNW - 1) {
     const int per = (T + S - 1) / S;
     const int t0 = min(T, slice * per), t1 = min(T, t0 + per);
@@ -298,6 +321,8 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     if (lane == 0) s_sw[warp] = s_sh[warp] = s_swh[warp] = 0.f;
   } else {
     float sw = 0.f, sh = 0.f, swh = 0.f;
+    uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mxx = 0u, mxy = 0u;
+    int nrect = 0, ninf = 0;
     for (int t = tid; t < T; t += kPrepThreads - 32) {
       const RasterBox rb = raster_box(boxes + (size_t)t * 7);
       if (t < ncache) {
@@ -307,16 +332,24 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
         c[10] = __int_as_float(rb.kind);
       }
       if (rb.kind == 1) {
-        atomicMin(&s_minx, f2ord(rb.x0));
-        atomicMax(&s_maxx, f2ord(rb.x1));
-        atomicMin(&s_miny, f2ord(rb.y0));
-        atomicMax(&s_maxy, f2ord(rb.y1));
-        atomicAdd(&s_nrect, 1);
+        mnx = min(mnx, f2ord(rb.x0)); mxx = max(mxx, f2ord(rb.x1));
+        mny = min(mny, f2ord(rb.y0)); mxy = max(mxy, f2ord(rb.y1));
+        ++nrect;
         const float w = rb.x1 - rb.x0, hgt = rb.y1 - rb.y0;
         sw += w; sh += hgt; swh += w * hgt;
       } else if (rb.kind == 2) {
-        atomicAdd(&s_ninf, 1);
+        ++ninf;
       }
+    }
+    // one shared-memory atomic per warp and quantity (redux.sync), not one per box
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    nrect = __reduce_add_sync(0xffffffffu, nrect); ninf = __reduce_add_sync(0xffffffffu, ninf);
+    if (lane == 0) {
+      atomicMin(&s_minx, mnx); atomicMax(&s_maxx, mxx);
+      atomicMin(&s_miny, mny); atomicMax(&s_maxy, mxy);
+      if (nrect) atomicAdd(&s_nrect, nrect);
+      if (ninf) atomicAdd(&s_ninf, ninf);
     }
     // fixed reduction tree: every slice of the frame computes bit-identical sums
 #pragma unroll
@@ -386,7 +419,7 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
   if (slice == 0 && tid == 0) reinterpret_cast<FrameHdr*>(ws + p.L.hdr)[f] = h;
 
   // ---- pass C: boxes touching this slice --------------------------------------------------
-  for (int i = tid; i < ncell; i += kPrepThreads) { cf[i] = 0u; word[i] = 0u; }
+  for (int i = tid; i < ncell; i += kPrepThreads) { cf[i] = 0u; word[i] = 0u; word2[i] = 0u; }
   for (int t = tid; t < T; t += kPrepThreads) {
     const RasterBox rb = get_box(t);
     if (rb.kind == 0) continue;
@@ -405,28 +438,35 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     for (int i = hw; i < nmine; i += kPrepThreads / 16) {
       const int t = mine[i];
       const RasterBox rb = get_box(t);
+      const SatBox sb = sat_box(rb, h);
       int cx0, cx1, cy0, cy1;
       cell_range(rb, h, cx0, cx1, cy0, cy1);
       const int y0 = max(cy0, row0), y1 = min(cy1, row1 - 1);
       for (int ty = y0 + yy; ty <= y1; ty += 4)
         for (int tx = cx0 + xx; tx <= cx1; tx += 4) {
           const bool border = (tx == 0) | (tx == G + 1) | (ty == 0) | (ty == G + 1);
-          if (border || rb.kind == 2 || sat_overlap(rb, h, tx, ty)) visit(t, (ty - row0) * Gp + tx);
+          if (border || rb.kind == 2 || sat_overlap(sb, h, tx, ty)) visit(t, (ty - row0) * Gp + tx);
         }
     }
   };
 
-  // ---- count pass -------------------------------------------------------------------------
-  raster([&](int, int c) { atomicAdd(&cf[c], 1u); });
+  // ---- the raster pass: count, and keep the first kInline candidates of every cell ---------
+  raster([&](int t, int c) {
+    const uint32_t k = atomicAdd(&cf[c], 1u);
+    if (k < 2u) atomicOr(&word[c], (uint32_t)t << (15u * k));
+    else if (k < (uint32_t)kInline) atomicOr(&word2[c], (uint32_t)t << (15u * (k - 2u)));
+  });
   __syncthreads();
 
-  // ---- scan: list space of the cells with >= 2 candidates ----------------------------------
+  // ---- scan: list space of the cells with >= 3 candidates ----------------------------------
   const int cpt = (ncell + kPrepThreads - 1) / kPrepThreads;
   const int c0 = min(ncell, tid * cpt), c1 = min(ncell, c0 + cpt);
   uint32_t need = 0;
+  bool big = false;
   for (int c = c0; c < c1; ++c) {
     const uint32_t n = cf[c];
-    if (n >= 2u) need += n + (n >= kCntLong ? 1u : 0u);
+    if (n >= 3u) need += n + (n >= kCntLong ? 1u : 0u);
+    big |= n > (uint32_t)kInline;
   }
   uint32_t incl = need;
 #pragma unroll
@@ -435,7 +475,7 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     if (lane >= o) incl += v;
   }
   if (lane == 31) s_warp_tot[warp] = incl;
-  __syncthreads();
+  const int any_big = __syncthreads_or(big ? 1 : 0);
   if (tid == 0) {
     uint32_t run = 0;
     for (int w = 0; w < kNW; ++w) {
@@ -451,37 +491,48 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     s_base = base;
   }
   __syncthreads();
+  const bool overflow = s_overflow != 0;
   {
-    const bool overflow = s_overflow != 0;
+    // final words; lists of <= kInline candidates are written straight from the inline slots
     uint32_t off = s_base + s_warp_tot[warp] + (incl - need);
     for (int c = c0; c < c1; ++c) {
       const uint32_t n = cf[c];
-      if (n >= 2u) {
+      const uint32_t w01 = word[c], w23 = word2[c];
+      uint32_t w = 0u;
+      if (n == 1u) {
+        w = (1u << kKindShift) | (w01 & kIdMask);
+      } else if (n == 2u) {
+        w = (2u << kKindShift) | (w01 & 0x3fffffffu);
+      } else if (n >= 3u) {
         if (overflow) {
-          word[c] = kCellAll;
+          w = kCellAll;
         } else {
           const bool lng = n >= kCntLong;
-          word[c] = ((lng ? kCntLong : n) << kCntShift) | off;
-          if (lng) ids[off] = (uint16_t)n;
+          w = (3u << kKindShift) | ((lng ? kCntLong : n) << kListCntShift) | off;
+          if (n <= (uint32_t)kInline) {
+            ids[off] = (uint16_t)(w01 & kIdMask);
+            ids[off + 1] = (uint16_t)((w01 >> 15) & kIdMask);
+            ids[off + 2] = (uint16_t)(w23 & kIdMask);
+            if (n == 4u) ids[off + 3] = (uint16_t)((w23 >> 15) & kIdMask);
+          } else {
+            if (lng) ids[off] = (uint16_t)n;
+            word2[c] = off + (lng ? 1u : 0u);  // where the fill pass writes this cell's list
+            cf[c] = n;                         // fill cursor in the upper half starts at 0
+          }
           off += n + (lng ? 1u : 0u);
         }
       }
+      word[c] = w;
     }
   }
-  __syncthreads();
-
-  // ---- fill pass ----------------------------------------------------------------------------
-  {
-    const bool overflow = s_overflow != 0;
+  // ---- fill pass, only when some cell of the slice holds more than kInline candidates ------
+  if (any_big && !overflow) {
+    __syncthreads();
     raster([&](int t, int c) {
-      const uint32_t old = atomicAdd(&cf[c], 0x10000u);
-      const uint32_t n = old & 0xffffu, k = old >> 16;
-      if (n == 1u) {
-        word[c] = (1u << kCntShift) | (uint32_t)t;
-      } else if (!overflow) {
-        const uint32_t w = word[c];
-        const uint32_t pos = (w & kPayMask) + ((w >> kCntShift) == kCntLong ? 1u : 0u) + k;
-        ids[pos] = (uint16_t)t;
+      const uint32_t n = cf[c] & 0xffffu;
+      if (n > (uint32_t)kInline) {
+        const uint32_t k = atomicAdd(&cf[c], 0x10000u) >> 16;
+        ids[word2[c] + k] = (uint16_t)t;
       }
     });
   }
@@ -504,6 +555,9 @@ struct StreamParams {
   int R, tb_base, tb_rem; // ranges of the frame-major batch list: range r has tb_base + (r < tb_rem) batches
   int slots;              // warps per range
   int vec4;
+  int smem_prep;          // the CTA keeps the contract terms of one frame in shared memory
+  int dynamic;            // warps draw their batches from the per-range counter (else static strides)
+  unsigned long long* trace;  // profiling hook: 16 globaltimer stamps per warp (NULL = off)
 };
 
 // Index data is written by the prep kernel of the same PDL chain: plain (coherent, L1-cached)
@@ -524,6 +578,19 @@ __device__ __forceinline__ float4 ld_f4(const float4* p) {
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
+}
+
+__device__ __forceinline__ void trace_stamp(const StreamParams& p, int k) {
+  if (p.trace && (threadIdx.x & 31) == 0 && k < 15) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.trace[((size_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 16 + k] = t;
+    if (k == 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      p.trace[((size_t)blockIdx.x * kWarps + (threadIdx.x >> 5)) * 16 + 15] = smid;
+    }
+  }
 }
 
 struct FrameCtx {
@@ -549,74 +616,95 @@ __device__ __forceinline__ int cell_of(float x, float y, const FrameCtx& h) {
   return pcell(y, h.gy0, h.invy, h.gp1) * h.Gp + pcell(x, h.gx0, h.invx, h.gp1);
 }
 
-constexpr int kQueue = 64;  // (point, candidate) pairs a warp batch resolves in lane-parallel passes
+// The exact test of every candidate of cell word `w` for the point (x, y, z) of this lane;
+// on_hit(t) for each enclosing box.  Sparse scenes take the two inline branches; the list
+// loop serves dense scenes, where every lane of the warp is busy in it anyway.
+// Contract terms of frame f: the CTA's shared-memory copy when it holds that frame, else global.
+__device__ __forceinline__ const float4* prep_of(const StreamParams& p, int f, int f_smem, const float4* prep_smem) {
+  return f == f_smem ? prep_smem : reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f * 2 * p.num_boxes;
+}
 
-// Per-lane fallback: runs the exact test for every candidate of the cell word, one lane per
-// point (dense scenes, long lists, pool overflow).
 template <typename F>
-__device__ __forceinline__ void for_each_hit(uint32_t w, const StreamParams& p, const FrameCtx& fc, float x,
+__device__ __forceinline__ void for_each_hit(uint32_t w, const StreamParams& p, int f, const float4* prep, float x,
                                              float y, float z, F on_hit) {
   if (w == 0u) return;
   const int T = p.num_boxes;
-  const float4* prep = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)fc.f * 2 * T;
+  const uint32_t kind = w >> kKindShift;
+  if (kind != 3u) {
+    const uint32_t t0 = w & kIdMask;
+    if (inside_box(x, y, z, prep[2 * t0], prep[2 * t0 + 1])) on_hit(t0);
+    if (kind == 2u) {
+      const uint32_t t1 = (w >> 15) & kIdMask;
+      if (inside_box(x, y, z, prep[2 * t1], prep[2 * t1 + 1])) on_hit(t1);
+    }
+    return;
+  }
   if (w == kCellAll) {
 #pragma unroll 1
     for (int t = 0; t < T; ++t)
-      if (inside_box(x, y, z, ld_f4(prep + 2 * t), ld_f4(prep + 2 * t + 1))) on_hit((uint32_t)t);
+      if (inside_box(x, y, z, prep[2 * t], prep[2 * t + 1])) on_hit((uint32_t)t);
     return;
   }
-  const uint16_t* ids = reinterpret_cast<const uint16_t*>(p.ws + p.L.ids) + (size_t)fc.f * p.L.cap;
-  uint32_t n = w >> kCntShift, base = w & kPayMask, t;
-  if (n == 1u) {
-    t = base;
-  } else {
-    if (n == kCntLong) {
-      n = ld_u16(ids + base);
-      ++base;
-    }
-    t = ld_u16(ids + base);
+  const uint16_t* ids = reinterpret_cast<const uint16_t*>(p.ws + p.L.ids) + (size_t)f * p.L.cap + (w & kListOffMask);
+  uint32_t n = (w >> kListCntShift) & 0x3ffu;
+  if (n == kCntLong) {
+    n = ld_u16(ids);
+    ++ids;
   }
 #pragma unroll 1
-  for (uint32_t j = 1;; ++j) {
-    if (inside_box(x, y, z, ld_f4(prep + 2 * t), ld_f4(prep + 2 * t + 1))) on_hit(t);
-    if (j >= n) break;
-    t = ld_u16(ids + base + j);
+  for (uint32_t j = 0; j < n; ++j) {
+    const uint32_t t = ld_u16(ids + j);
+    if (inside_box(x, y, z, prep[2 * t], prep[2 * t + 1])) on_hit(t);
   }
 }
 
 // WS > 0: row words known at compile time (the common shapes), 0: taken from the params.
-// Each warp owns the batches slot, slot + slots, ... of its range (static: with ~5 batches
-// per warp at the training shape a dynamic scheduler costs more than it balances).
-template <int MODE, int WS>
+// Work split: the frame-major list of P-point batches is cut into R contiguous ranges, range
+// r is served by the CTAs with blockIdx % R == r (one SM's worth, sharing the frame's index in
+// L1); warp `slot` of a range owns its batches slot, slot + slots, ... (static strides).
+// Measured alternatives at the training shape: per-range L2 counters (+5 us:
+// 80 same-address atomics per range at kernel start), CTA-local shared-memory counters (+2 us),
+// a cp.async ring for the points (-0.5 us, +smem), two points per lane (same time), spreading
+// a warp's batches over the frame (same time) — the kernel is instruction-issue bound with a
+// tail of slow warps, not bandwidth bound.
+// Software pipeline per warp: the points of batch n+2 are in flight, the cell word of batch
+// n+1 is requested, batch n is tested and written.
+template <int MODE, int WS, bool VEC4>
 __global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const StreamParams p) {
   extern __shared__ __align__(16) uint32_t smem_all[];
+  trace_stamp(p, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int W = MODE == kModePart ? 1 : (WS > 0 ? WS : p.row_words);
+  const int W = WS > 0 ? WS : p.row_words;
   const int P = (MODE == kModePart || WS > 0) ? 32 : p.batch_pts;
-  const int N = p.num_points, bpf = p.batches_per_frame;
+  const int N = p.num_points, bpf = p.batches_per_frame, slots = p.slots;
   const int stage_words = P * W;
-  uint32_t* stage = smem_all + (size_t)warp * (stage_words + kQueue + 4);
-  uint32_t* queue = stage + stage_words;
-  uint32_t* qcount = queue + kQueue;
+  // shared memory: [contract terms of one frame: 2 T float4, when they fit][per-warp stages]
+  const int prep_words = p.smem_prep ? 8 * p.num_boxes : 0;
+  const float4* prep_smem = reinterpret_cast<const float4*>(smem_all);
+  uint32_t* stage = smem_all + prep_words + (size_t)warp * stage_words;
 
   const int r = blockIdx.x % p.R, slot = (int)(blockIdx.x / p.R) * kWarps + warp;
-  const int nb = p.tb_base + (r < p.tb_rem ? 1 : 0);                  // batches of this range
-  const int g0 = r * p.tb_base + min(r, p.tb_rem);                    // first batch of the range
-  int i = slot;                                                       // batch index inside the range
-  int f = 0, c = 0;                                                   // frame / batch inside the frame
-  if (i < nb) {
-    f = (g0 + i) / bpf;
-    c = (g0 + i) - f * bpf;
-  }
-  auto advance = [&](int& ff, int& cc) {
-    cc += p.slots;
-    while (cc >= bpf) { cc -= bpf; ++ff; }
+  const int nb = p.tb_base + (r < p.tb_rem ? 1 : 0);  // batches of this range
+  const int g0 = r * p.tb_base + min(r, p.tb_rem);    // first batch of the range
+  const int rf0 = g0 / bpf, rc0 = g0 - rf0 * bpf;     // its frame / batch inside the frame
+  // the frame whose contract terms this CTA keeps in shared memory: that of its first batch
+  const int f_smem = p.smem_prep ? min(p.num_frames - 1, (g0 + (int)(blockIdx.x / p.R) * kWarps) / bpf) : -1;
+
+  struct Batch { int f, c; };  // frame, batch inside the frame; f < 0: none
+  auto decode = [&](int b) -> Batch {  // b: batch index inside the range, or < 0
+    Batch t;
+    t.f = -1; t.c = 0;
+    if (b >= 0 && b < nb) {
+      t.f = rf0; t.c = rc0 + b;
+      while (t.c >= bpf) { t.c -= bpf; ++t.f; }
+    }
+    return t;
   };
-  auto fetch = [&](bool live, int ff, int cc, float& fx, float& fy, float& fz) {
-    const int pt = cc * P + lane;
-    if (live && lane < P && pt < N) {
-      const size_t idx = (size_t)ff * N + pt;
-      if (p.vec4) {
+  auto fetch = [&](const Batch& t, float& fx, float& fy, float& fz) {
+    const int pt = t.c * P + lane;
+    if (t.f >= 0 && lane < P && pt < N) {
+      const size_t idx = (size_t)t.f * N + pt;
+      if constexpr (VEC4) {
         const float4 v = __ldcs(reinterpret_cast<const float4*>(p.points) + idx);
         fx = v.x; fy = v.y; fz = v.z;
       } else {
@@ -625,134 +713,129 @@ __global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const 
       }
     }
   };
-  // two batches of points in flight per warp, requested before the index is ready
+  // static first batch, requested before the index is ready
+  Batch cur = decode(slot), nxt;
   float x = 0.f, y = 0.f, z = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
-  int f1 = f, c1 = c;
-  fetch(i < nb, f, c, x, y, z);
-  advance(f1, c1);
-  fetch(i + p.slots < nb, f1, c1, x1, y1, z1);
+  fetch(cur, x, y, z);
 
+  trace_stamp(p, 1);
   // everything below reads what the prep kernel wrote
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  trace_stamp(p, 2);
+  // batch draws: after its static batch a warp takes batches from its CTA's slab of the range
+  // through a shared-memory counter (fast warps relieve slow ones; an L2 counter per range was
+  // measured slower: 80 same-address atomics per range at kernel start cost ~5 us)
+  __shared__ uint32_t s_draw;
+  const bool dynamic = p.dynamic != 0 && cur.f >= 0;  // a warp without a static batch (tiny inputs) stays idle
+  const int ncta = (int)((gridDim.x - 1 - (unsigned)r) / (unsigned)p.R) + 1;  // CTAs serving this range
+  const int dyn_total = max(0, nb - slots);
+  const int per_cta = (dyn_total + ncta - 1) / ncta;
+  const int slab0 = slots + (int)(blockIdx.x / p.R) * per_cta, slab1 = min(nb, slab0 + per_cta);
+  int static_next = slot + slots;  // static mode: strided batches
+  auto draw = [&]() -> int {
+    if (!dynamic) { const int b = static_next; static_next += slots; return b; }
+    uint32_t k = 0;
+    if (lane == 0) k = atomicAdd(&s_draw, 1u);
+    const int b = slab0 + (int)__shfl_sync(0xffffffffu, k, 0);
+    return b < slab1 ? b : -1;
+  };
+  if (threadIdx.x == 0) s_draw = 0u;
   if (blockIdx.x == 0 && threadIdx.x < 32) {  // hand the id-pool cursors back zeroed
     uint32_t* used = reinterpret_cast<uint32_t*>(p.ws + p.L.ids_used);
     for (int q = lane; q < p.num_frames; q += 32) used[q] = 0u;
   }
+  if (p.smem_prep) {
+    const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f_smem * 2 * p.num_boxes;
+    float4* dst = reinterpret_cast<float4*>(smem_all);
+    for (int k = threadIdx.x; k < 2 * p.num_boxes; k += kStreamThreads) dst[k] = ld_f4(src + k);
+  }
+  __syncthreads();
 
-  int cur_f = -1;
   FrameCtx fc;
+  fc.f = -1;
+  auto lookup = [&](const Batch& t, float lx, float ly) -> uint32_t {
+    if (t.f < 0) return 0u;
+    if (t.f != fc.f) fc = load_frame(p, t.f);
+    return (lane < P && t.c * P + lane < N) ? ld_u32(fc.grid + cell_of(lx, ly, fc)) : 0u;
+  };
+  nxt = decode(cur.f >= 0 ? draw() : -1);
+  fetch(nxt, x1, y1, z1);
+  uint32_t wn = lookup(cur, x, y);
+  trace_stamp(p, 3);
+  int tk = 4;
+
 #pragma unroll 1
-  for (; i < nb; i += p.slots) {
-    if (f != cur_f) {
-      fc = load_frame(p, f);
-      cur_f = f;
-    }
-    const int pt0 = c * P;
+  while (cur.f >= 0) {
+    const int bf = cur.f, pt0 = cur.c * P;
     const int nvalid = min(P, N - pt0);
-    const bool valid = lane < nvalid;
     const float cx = x, cy = y, cz = z;
-    const int bf = f;
-    // rotate the pipeline and request the batch after next
+    const uint32_t w = wn;
+    // rotate the pipeline
     x = x1; y = y1; z = z1;
-    f = f1; c = c1;
-    advance(f1, c1);
-    fetch(i + 2 * p.slots < nb, f1, c1, x1, y1, z1);
+    cur = nxt;
+    nxt = decode(cur.f >= 0 ? draw() : -1);  // batch n+2
+    fetch(nxt, x1, y1, z1);
+    wn = lookup(cur, x, y);
 
-    const uint32_t w = valid ? ld_u32(fc.grid + cell_of(cx, cy, fc)) : 0u;
-
-    // zero the warp's stage (bits / all: the linear image of its P rows; part: min box index)
     if constexpr (MODE == kModePart) {
-      stage[lane] = 0xffffffffu;
-    } else if constexpr (WS > 0) {
-#pragma unroll
-      for (int k = 0; k < (32 * WS) / 128; ++k) reinterpret_cast<uint4*>(stage)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
-      if ((32 * WS) % 128 != 0 && lane < (32 * WS % 128) / 4)
-        reinterpret_cast<uint4*>(stage)[(32 * WS) / 128 * 32 + lane] = make_uint4(0, 0, 0, 0);
+      uint32_t best = 0xffffffffu;
+      for_each_hit(w, p, bf, prep_of(p, bf, f_smem, prep_smem), cx, cy, cz, [&](uint32_t t) { best = min(best, t); });
+      if (lane < nvalid) __stcs(reinterpret_cast<int32_t*>(p.out) + (size_t)bf * N + pt0 + lane, (int32_t)best);
     } else {
-#pragma unroll 1
-      for (int k = lane; k < (stage_words >> 2); k += 32) reinterpret_cast<uint4*>(stage)[k] = make_uint4(0, 0, 0, 0);
-    }
-    if (lane == 0) *qcount = 0u;
-    __syncwarp();
-    // reserve queue space for this lane's candidates
-    uint32_t cnt = w >> kCntShift;
-    if (cnt == kCntLong) cnt = kQueue + 1;  // long list or pool overflow: per-lane path
-    const uint32_t pos = cnt ? atomicAdd(qcount, cnt) : 0u;
-    __syncwarp();
-    const uint32_t total = *qcount;
-    auto mark = [&](uint32_t row, uint32_t t, bool own) {
-      if constexpr (MODE == kModePart) {
-        if (own) stage[row] = min(stage[row], t);
-        else atomicMin(&stage[row], t);
+      // zero the warp's stage (the linear image of its P rows), mark the hits, copy out
+      if constexpr (WS > 0) {
+#pragma unroll
+        for (int k = 0; k < (32 * WS) / 128; ++k) reinterpret_cast<uint4*>(stage)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
+        if ((32 * WS) % 128 != 0 && lane < (32 * WS % 128) / 4)
+          reinterpret_cast<uint4*>(stage)[(32 * WS) / 128 * 32 + lane] = make_uint4(0, 0, 0, 0);
       } else {
-        if (own) stage[row * W + (t >> 5)] |= 1u << (t & 31u);
-        else atomicOr(&stage[row * W + (t >> 5)], 1u << (t & 31u));
-      }
-    };
-    if (total <= kQueue) {
-      // expand (point, candidate) pairs, then test them one pair per lane
-      if (cnt == 1u) {
-        queue[pos] = ((uint32_t)lane << 16) | (w & kPayMask);
-      } else if (cnt > 1u) {
-        const uint16_t* ids = reinterpret_cast<const uint16_t*>(p.ws + p.L.ids) + (size_t)bf * p.L.cap + (w & kPayMask);
 #pragma unroll 1
-        for (uint32_t j = 0; j < cnt; ++j) queue[pos + j] = ((uint32_t)lane << 16) | ld_u16(ids + j);
+        for (int k = lane; k < (stage_words >> 2); k += 32) reinterpret_cast<uint4*>(stage)[k] = make_uint4(0, 0, 0, 0);
       }
       __syncwarp();
-      const float4* prep = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)bf * 2 * p.num_boxes;
-#pragma unroll 1
-      for (uint32_t q0 = 0; q0 < total; q0 += 32) {
-        const bool have = q0 + lane < total;
-        const uint32_t e = have ? queue[q0 + lane] : 0u;
-        const uint32_t src = e >> 16, t = e & 0xffffu;
-        const float px = __shfl_sync(0xffffffffu, cx, src), py = __shfl_sync(0xffffffffu, cy, src),
-                    pz = __shfl_sync(0xffffffffu, cz, src);
-        if (have && inside_box(px, py, pz, ld_f4(prep + 2 * t), ld_f4(prep + 2 * t + 1))) mark(src, t, false);
-      }
-    } else {
-      for_each_hit(w, p, fc, cx, cy, cz, [&](uint32_t t) { mark((uint32_t)lane, t, true); });
-    }
-    __syncwarp();
-
-    if constexpr (MODE == kModePart) {
-      if (valid) __stcs(reinterpret_cast<int32_t*>(p.out) + (size_t)bf * N + pt0 + lane, (int32_t)stage[lane]);
-    } else if constexpr (MODE == kModeBits) {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(p.out) + ((size_t)bf * N + pt0) * W;
-      const int nw = nvalid * W;
-      if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-        const int n4 = nw >> 2;
-        if (WS > 0 && nvalid == 32 && (32 * WS) % 128 == 0) {
+      for_each_hit(w, p, bf, prep_of(p, bf, f_smem, prep_smem), cx, cy, cz,
+                   [&](uint32_t t) { stage[lane * W + (t >> 5)] |= 1u << (t & 31u); });
+      __syncwarp();
+      if constexpr (MODE == kModeBits) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p.out) + ((size_t)bf * N + pt0) * W;
+        const int nw = nvalid * W;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+          const int n4 = nw >> 2;
+          if (WS > 0 && nvalid == 32 && (32 * WS) % 128 == 0) {
 #pragma unroll
-          for (int k = 0; k < (32 * WS) / 128; ++k)
-            __stcs(reinterpret_cast<uint4*>(dst) + k * 32 + lane, reinterpret_cast<const uint4*>(stage)[k * 32 + lane]);
-        } else {
+            for (int k = 0; k < (32 * WS) / 128; ++k)
+              __stcs(reinterpret_cast<uint4*>(dst) + k * 32 + lane, reinterpret_cast<const uint4*>(stage)[k * 32 + lane]);
+          } else {
 #pragma unroll 1
-          for (int k = lane; k < n4; k += 32)
-            __stcs(reinterpret_cast<uint4*>(dst) + k, reinterpret_cast<const uint4*>(stage)[k]);
-          for (int k = (n4 << 2) + lane; k < nw; k += 32) __stcs(dst + k, stage[k]);
-        }
-      } else {
-        for (int k = lane; k < nw; k += 32) __stcs(dst + k, stage[k]);
-      }
-    } else {  // kModeAll: int32 [N, T] rows, lane l writes boxes 4l..4l+3 (+128 k)
-      const int T = p.num_boxes;
-      int32_t* dst = reinterpret_cast<int32_t*>(p.out) + ((size_t)bf * N + pt0) * T;
-      if ((T & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
-        for (int q = 0; q < nvalid; ++q) {
-          for (int t4 = lane * 4; t4 < T; t4 += 128) {
-            const uint32_t nib = stage[q * W + (t4 >> 5)] >> (t4 & 31);
-            __stcs(reinterpret_cast<int4*>(dst + (size_t)q * T + t4),
-                   make_int4(nib & 1u, (nib >> 1) & 1u, (nib >> 2) & 1u, (nib >> 3) & 1u));
+            for (int k = lane; k < n4; k += 32)
+              __stcs(reinterpret_cast<uint4*>(dst) + k, reinterpret_cast<const uint4*>(stage)[k]);
+            for (int k = (n4 << 2) + lane; k < nw; k += 32) __stcs(dst + k, stage[k]);
           }
+        } else {
+          for (int k = lane; k < nw; k += 32) __stcs(dst + k, stage[k]);
         }
-      } else {
-        for (int q = 0; q < nvalid; ++q)
-          for (int t = lane; t < T; t += 32)
-            __stcs(dst + (size_t)q * T + t, (int32_t)((stage[q * W + (t >> 5)] >> (t & 31)) & 1u));
+      } else {  // kModeAll: int32 [N, T] rows, lane l writes boxes 4l..4l+3 (+128 k)
+        const int T = p.num_boxes;
+        int32_t* dst = reinterpret_cast<int32_t*>(p.out) + ((size_t)bf * N + pt0) * T;
+        if ((T & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+          for (int q = 0; q < nvalid; ++q) {
+            for (int t4 = lane * 4; t4 < T; t4 += 128) {
+              const uint32_t nib = stage[q * W + (t4 >> 5)] >> (t4 & 31);
+              __stcs(reinterpret_cast<int4*>(dst + (size_t)q * T + t4),
+                     make_int4(nib & 1u, (nib >> 1) & 1u, (nib >> 2) & 1u, (nib >> 3) & 1u));
+            }
+          }
+        } else {
+          for (int q = 0; q < nvalid; ++q)
+            for (int t = lane; t < T; t += 32)
+              __stcs(dst + (size_t)q * T + t, (int32_t)((stage[q * W + (t >> 5)] >> (t & 31)) & 1u));
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
+    trace_stamp(p, tk++);
   }
+  trace_stamp(p, 14);
 }
 
 __global__ void sincos_test_kernel(const float* __restrict__ x, long long n, float* sn, float* cs) {
@@ -775,14 +858,14 @@ __global__ void box_prep_test_kernel(const float* __restrict__ boxes, int T, flo
   }
 }
 
-template <int MODE, int WS>
+template <int MODE, int WS, bool VEC4>
 int launch_stream(const StreamParams& p, int grid, size_t smem, cudaStream_t st) {
   static int configured[64];
   int dev = 0;
   GGA_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && (int)smem > configured[dev] && smem > 48 * 1024) {
     GGA_CHECK_CUDA(
-        cudaFuncSetAttribute(pib_stream_kernel<MODE, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(pib_stream_kernel<MODE, WS, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = (int)smem;
   }
   cudaLaunchConfig_t cfg = {};
@@ -795,7 +878,7 @@ int launch_stream(const StreamParams& p, int grid, size_t smem, cudaStream_t st)
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_kernel<MODE, WS>, p));
+  GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_kernel<MODE, WS, VEC4>, p));
   return GGA_OK;
 }
 
@@ -831,6 +914,7 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
 
   StreamParams sp;
   sp.points = points; sp.out = out; sp.ws = static_cast<unsigned char*>(workspace); sp.L = L;
+  sp.trace = g_trace;
   sp.pts_stride = pts_stride; sp.num_points = num_points; sp.num_boxes = num_boxes; sp.num_frames = B;
   sp.row_words = gga_pib_row_words(num_boxes);
   sp.batch_pts = sp.row_words <= 32 ? 32 : (1024 / sp.row_words < 1 ? 1 : 1024 / sp.row_words);
@@ -845,10 +929,13 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   sp.R = (int)R;
   sp.tb_base = (int)(tb / R);
   sp.tb_rem = (int)(tb % R);
+  sp.dynamic = g_tune_dynamic ? 1 : 0;
+  GGA_REQUIRE(sp.R <= kMaxRanges, "too many ranges");
   sp.vec4 = (pts_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0) ? 1 : 0;
   const int grid = (int)R * occ;
-  const int stage_words = mode == kModePart ? 32 : sp.row_words * sp.batch_pts;
-  const size_t smem = (size_t)(stage_words + kQueue + 4) * 4 * kWarps;
+  sp.smem_prep = num_boxes <= 512 ? 1 : 0;
+  const size_t smem = (mode == kModePart ? 0 : (size_t)sp.row_words * sp.batch_pts * 4 * kWarps) +
+                      (sp.smem_prep ? (size_t)num_boxes * 32 : 0);
   GGA_REQUIRE(smem <= 200 * 1024, "row too wide for the stage");
 
   // prep: S slices per frame
@@ -863,7 +950,7 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   PrepParams pp;
   pp.boxes = boxes; pp.ws = sp.ws; pp.L = L; pp.T = num_boxes;
   pp.ncache = num_boxes < 2048 ? num_boxes : 2048;
-  const size_t prep_smem = (size_t)2 * (kMaxSliceCells + 4) * 4 + align_up((size_t)num_boxes * 2, 16) +
+  const size_t prep_smem = (size_t)3 * (kMaxSliceCells + 4) * 4 + align_up((size_t)num_boxes * 2, 16) +
                            (size_t)pp.ncache * kBoxWords * 4;
   {
     static int configured[64];
@@ -875,16 +962,22 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
       configured[dev] = (int)prep_smem;
     }
   }
-  pib_prep_kernel<<<dim3(S, B), kPrepThreads, prep_smem, st>>>(pp);
-  GGA_CHECK_CUDA(cudaGetLastError());
+  if (g_tune_phase != 2) {
+    pib_prep_kernel<<<dim3(S, B), kPrepThreads, prep_smem, st>>>(pp);
+    GGA_CHECK_CUDA(cudaGetLastError());
+  }
+  if (g_tune_phase == 1) return GGA_OK;
 
   if (mode == kModeBits) {
-    if (sp.row_words == 8) return launch_stream<kModeBits, 8>(sp, grid, smem, st);
-    if (sp.row_words == 2) return launch_stream<kModeBits, 2>(sp, grid, smem, st);
-    return launch_stream<kModeBits, 0>(sp, grid, smem, st);
+    if (sp.vec4) {
+      if (sp.row_words == 8) return launch_stream<kModeBits, 8, true>(sp, grid, smem, st);
+      if (sp.row_words == 2) return launch_stream<kModeBits, 2, true>(sp, grid, smem, st);
+      return launch_stream<kModeBits, 0, true>(sp, grid, smem, st);
+    }
+    return launch_stream<kModeBits, 0, false>(sp, grid, smem, st);
   }
-  if (mode == kModeAll) return launch_stream<kModeAll, 0>(sp, grid, smem, st);
-  return launch_stream<kModePart, 0>(sp, grid, smem, st);
+  if (mode == kModeAll) return launch_stream<kModeAll, 0, false>(sp, grid, smem, st);
+  return launch_stream<kModePart, 0, false>(sp, grid, smem, st);
 }
 
 }  // namespace
@@ -899,7 +992,20 @@ extern "C" int gga_pib_row_words(int num_boxes) {
 
 extern "C" int gga_pib_set_tuning(int grid_cells, int ctas_per_sm) {
   g_tune_grid = grid_cells;
-  g_tune_occ = ctas_per_sm;
+  g_tune_dynamic = ctas_per_sm < 0 ? 1 : 0;  // negative: CTA-local dynamic batch draws instead of static strides (experiment hook)
+  g_tune_occ = ctas_per_sm < 0 ? -ctas_per_sm : ctas_per_sm;
+  return GGA_OK;
+}
+
+/* profiling hook: device buffer of 16 x uint64 per stream-kernel warp (globaltimer ns, last word = smid) */
+extern "C" int gga_test_pib_trace(void* buf) {
+  g_trace = static_cast<unsigned long long*>(buf);
+  return GGA_OK;
+}
+
+/* profiling hook: 0 = both kernels, 1 = index build only, 2 = streaming only (reuses the index in the workspace) */
+extern "C" int gga_test_pib_phase(int phase) {
+  g_tune_phase = phase;
   return GGA_OK;
 }
 

@@ -192,6 +192,12 @@ int gga_image_box_overlap_f64(const double* boxes, int N, const double* query, i
 /* ------------------------------------------------------------------------------------
  * Test hooks (device build of include/gga_detmath.h and of the per-box preparation).
  * ---------------------------------------------------------------------------------- */
+/* profiling hook: 0 = both membership kernels, 1 = index build only, 2 = streaming only
+ * (reuses the index already in the workspace; results are only valid for phase 0) */
+int gga_test_pib_phase(int phase);
+/* profiling hook: device buffer receiving 16 x uint64 per warp of the streaming kernel
+ * (globaltimer stamps; word 15 = SM id); NULL switches tracing off */
+int gga_test_pib_trace(void* device_buffer);
 int gga_test_sincos(const float* x, int64_t n, float* sn, float* cs, void* stream);
 /* prep : float [num_boxes, 8] = (cx, cy, cz_centre, hz, cosa, sina, hx, hy) */
 int gga_test_box_prep(const float* boxes, int num_boxes, float* prep, void* stream);

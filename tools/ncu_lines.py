@@ -6,6 +6,11 @@ rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25; filt = s
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source=cuda,sass'],
                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+def num(v):
+    try:
+        return int(float(v))
+    except Exception:
+        return 0
 seen = set()
 i = 0
 while i < len(rows):
@@ -22,11 +27,11 @@ while i < len(rows):
         seen.add(name)
         si, ii = hdr.index('# Samples'), hdr.index('Instructions Executed')
         stall_cols = [k for k, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
-        tot_s = sum(int(l[si] or 0) for l in lines) or 1; tot_i = sum(int(l[ii] or 0) for l in lines) or 1
+        tot_s = sum(num(l[si]) for l in lines) or 1; tot_i = sum(num(l[ii]) for l in lines) or 1
         print(f'## {name[:100]}  samples={tot_s} warp-instr={tot_i}')
-        for l in sorted(lines, key=lambda l: -int(l[(ii if "--by-ins" in sys.argv else si)] or 0))[:top]:
-            st = sorted(((int(l[k] or 0), hdr[k][6:]) for k in stall_cols), reverse=True)[:3]
+        for l in sorted(lines, key=lambda l: -num(l[(ii if "--by-ins" in sys.argv else si)]))[:top]:
+            st = sorted(((num(l[k]), hdr[k][6:]) for k in stall_cols), reverse=True)[:3]
             sts = ' '.join(f'{n}:{v}' for v, n in st if v)
-            print(f'{l[0]:>5s} smp {100*int(l[si] or 0)/tot_s:5.1f}% ins {100*int(l[ii] or 0)/tot_i:5.1f}% | {l[1].strip()[:95]:95s} | {sts}')
+            print(f'{l[0]:>5s} smp {100*num(l[si])/tot_s:5.1f}% ins {100*num(l[ii])/tot_i:5.1f}% | {l[1].strip()[:95]:95s} | {sts}')
     else:
         i += 1

@@ -34,6 +34,7 @@ def main():
     ap.add_argument('--unsorted', action='store_true')
     ap.add_argument('--grids', default='0,8,16,24,32,40,48,64')
     ap.add_argument('--ctas', default='0')
+    ap.add_argument('--phase', type=int, default=0)
     a = ap.parse_args()
     c = synth.CONFIGS[a.cfg]
     pool = []
@@ -50,18 +51,27 @@ def main():
     for g in [int(x) for x in a.grids.split(',')]:
         for ct in [int(x) for x in a.ctas.split(',')]:
             G.ops.set_tuning(g, ct)
-            it = [0]
+            wss = [torch.zeros((int(L.gga_pib_workspace_bytes(a.frames, N, M)),), dtype=torch.uint8, device='cuda')
+                   for _ in range(a.pool)]
 
-            def fn():
-                p, b = pool[it[0] % a.pool]
-                o = outs[it[0] % a.pool]
-                it[0] += 1
-                ws = G.ops.workspace(p.device, a.frames, N, M)
+            def call(k):
+                p, b = pool[k % a.pool]
+                o, ws = outs[k % a.pool], wss[k % a.pool]
                 rc = L.gga_points_in_boxes_bits(p.data_ptr(), 4, b.data_ptr(), o.data_ptr(), a.frames, N, M,
-                                                ws.data_ptr(), ws.numel(), st)
+                                                ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
                 assert rc == 0
-            ms = time_ms(fn)
-            r = dict(cfg=a.cfg, grid=g, ctas=ct, ms=round(ms, 4), gbs=round(bytes_step / ms / 1e6, 1),
+            for k in range(a.pool):
+                call(k)
+            torch.cuda.synchronize()
+            L.gga_test_pib_phase(a.phase)
+            reps = 4 * a.pool
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):     # GPU-bound timing: the launches are replayed by the driver
+                for k in range(reps):
+                    call(k)
+            ms = time_ms(g_.replay, iters=10, warm=2) / reps
+            L.gga_test_pib_phase(0)
+            r = dict(cfg=a.cfg, phase=a.phase, grid=g, ctas=ct, ms=round(ms, 4), gbs=round(bytes_step / ms / 1e6, 1),
                      frames_per_s=round(a.frames / ms * 1e3, 1))
             print(json.dumps(r), flush=True)
             res.append(r)
