@@ -67,18 +67,7 @@ class GeometryStep:
                                               self.bits.data_ptr(), self.F, self.N, self.M,
                                               self.ws.data_ptr(), self.ws.numel(), st),
                    'points_in_boxes_bits')
-        a = _lib.BoxLossArgs()
-        a.boxes = boxes.data_ptr()
-        a.proj = lidar2img.data_ptr()
-        a.proj_stride = 16 if lidar2img.dim() > 2 else 0
-        a.target = target.data_ptr()
-        if weight is not None:
-            a.weight, a.weight_cols = weight.data_ptr(), 1
-        a.n, a.mode, a.loss_kind = n, self.mode, self.kind
-        a.depth_clamp, a.eps = self.depth_clamp, self.eps
-        a.grad_scale = self.loss_weight / float(avg_factor if avg_factor is not None else max(n, 1))
-        a.box2d, a.loss, a.loss_sum = self.box2d.data_ptr(), self.loss.data_ptr(), self.loss_sum.data_ptr()
-        a.grad_boxes = self.grad_boxes.data_ptr()
+        a = self._box_args(boxes, lidar2img, target, weight, avg_factor)
         _lib.check(L.gga_box_project_loss(a, self.side.cuda_stream), 'box_project_loss')
         join = torch.cuda.Event()
         join.record(self.side)
@@ -103,10 +92,32 @@ class GeometryStep:
         self.graph.replay()
 
     # ------------------------------------------------------------------ host-buffer step
-    def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None):
+    def _box_args(self, boxes, lidar2img, target, weight, avg_factor):
+        n = self.F * self.M
+        a = _lib.BoxLossArgs()
+        a.boxes = boxes.data_ptr()
+        a.proj = lidar2img.data_ptr()
+        a.proj_stride = 16 if lidar2img.dim() > 2 else 0
+        a.target = target.data_ptr()
+        if weight is not None:
+            a.weight, a.weight_cols = weight.data_ptr(), 1
+        a.n, a.mode, a.loss_kind = n, self.mode, self.kind
+        a.depth_clamp, a.eps = self.depth_clamp, self.eps
+        a.grad_scale = self.loss_weight / float(avg_factor if avg_factor is not None else max(n, 1))
+        a.box2d, a.loss, a.loss_sum = self.box2d.data_ptr(), self.loss.data_ptr(), self.loss_sum.data_ptr()
+        a.grad_boxes = self.grad_boxes.data_ptr()
+        return a
+
+    def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3):
         """Same step with HOST inputs (pinned torch CPU tensors) and HOST results: returns
-        (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous."""
+        (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous.
+
+        The PCIe link is the bound (46 MB per step at the training shape), so the step is
+        pipelined frame by frame over `n_streams` streams: the H2D copy of frame f+1, the
+        membership kernels of frame f and the D2H copy of the masks of frame f-1 overlap
+        (full-duplex link); the box kernel and its small copies run on the calling stream."""
         dev = self.device
+        L = self.L
         if self._host is None:
             h = {}
             for name, t in (('points', points), ('boxes', boxes), ('lidar2img', lidar2img),
@@ -115,18 +126,37 @@ class GeometryStep:
             h['h_bits'] = torch.empty(self.bits.shape, dtype=torch.int32).pin_memory()
             h['h_grad'] = torch.empty(self.grad_boxes.shape, dtype=torch.float32).pin_memory()
             h['h_loss'] = torch.empty((1,), dtype=torch.float32).pin_memory()
+            h['streams'] = [torch.cuda.Stream(device=dev) for _ in range(max(1, n_streams))]
+            wb = int(L.gga_pib_workspace_bytes(1, self.N, self.M))
+            h['ws'] = [torch.zeros((wb,), dtype=torch.uint8, device=dev) for _ in h['streams']]
             self._host = h
         h = self._host
-        h['d_points'].copy_(points, non_blocking=True)
+        cur = torch.cuda.current_stream(dev)
         h['d_boxes'].copy_(boxes, non_blocking=True)
+        boxes_ready = torch.cuda.Event()
+        boxes_ready.record(cur)
+        # membership, one frame per pipeline slot
+        for f in range(self.F):
+            st, ws = h['streams'][f % len(h['streams'])], h['ws'][f % len(h['streams'])]
+            st.wait_event(boxes_ready)
+            with torch.cuda.stream(st):
+                h['d_points'][f].copy_(points[f], non_blocking=True)
+                _lib.check(L.gga_points_in_boxes_bits(h['d_points'][f].data_ptr(), self.pts_stride,
+                                                      h['d_boxes'][f].data_ptr(), self.bits[f].data_ptr(), 1,
+                                                      self.N, self.M, ws.data_ptr(), ws.numel(), st.cuda_stream),
+                           'points_in_boxes_bits')
+                h['h_bits'][f].copy_(self.bits[f], non_blocking=True)
+        # projection + loss forward/backward on the calling stream
         h['d_lidar2img'].copy_(lidar2img, non_blocking=True)
         h['d_target'].copy_(target, non_blocking=True)
         h['d_weight'].copy_(weight, non_blocking=True)
-        self.run(h['d_points'], h['d_boxes'], h['d_lidar2img'], h['d_target'], h['d_weight'], avg_factor)
-        h['h_bits'].copy_(self.bits, non_blocking=True)
+        a = self._box_args(h['d_boxes'], h['d_lidar2img'], h['d_target'], h['d_weight'], avg_factor)
+        _lib.check(L.gga_box_project_loss(a, cur.cuda_stream), 'box_project_loss')
         h['h_grad'].copy_(self.grad_boxes, non_blocking=True)
         h['h_loss'].copy_(self.loss_sum, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
+        for st in h['streams']:
+            cur.wait_stream(st)
+        cur.synchronize()
         return h['h_bits'], float(h['h_loss'][0]), h['h_grad']
 
     def host_bytes(self, points, boxes, lidar2img, target, weight):

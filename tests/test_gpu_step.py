@@ -1,0 +1,107 @@
+"""GPU parity tests of the training-shaped step (gga_b200/step.py): membership bits, loss and
+gradients of one GeometryStep against the CPU oracle; CUDA-graph replay and the host-buffer
+(pipelined H2D / kernels / D2H) variant must give identical results."""
+import numpy as np
+import pytest
+import torch
+
+import gga_b200 as G
+from gga_b200 import synth
+from gga_b200.step import GeometryStep
+from oracle import geometry as og
+from oracle import losses as ol
+from oracle import membership as om
+
+pytestmark = pytest.mark.gpu
+F, N, M = 3, 6000, 200
+
+
+def _batch():
+    bt = synth.make_batch(2, 40, F, N=N, M=M)
+    return {k: np.ascontiguousarray(bt[k]) for k in ('points', 'boxes', 'lidar2img', 'target', 'weight')}
+
+
+def _oracle(bt):
+    masks = np.stack([om.points_in_boxes_all_np(bt['points'][f], bt['boxes'][f], 8) for f in range(F)])
+    b = torch.from_numpy(bt['boxes']).reshape(-1, 7).clone().requires_grad_(True)
+    box2d = og.project_lidar_direct(b, torch.from_numpy(bt['lidar2img']).reshape(-1, 4, 4))
+    loss = ol.giou_loss_module(box2d, torch.from_numpy(bt['target']).reshape(-1, 4),
+                               torch.from_numpy(bt['weight']).reshape(-1), avg_factor=float(F * M))
+    loss.backward()
+    return masks, float(loss), b.grad.numpy()
+
+
+def _check(step, bits, loss_sum, grad, ref):
+    masks, rloss, rgrad = ref
+    got = G.unpack_bits(torch.as_tensor(bits).cuda(), M).cpu().numpy()
+    assert np.array_equal(got, masks)                                  # bit-exact
+    loss = float(loss_sum) / (F * M)
+    assert abs(loss - rloss) <= 1e-5 * abs(rloss) + 1e-7                # 1e-5 relative (north_star)
+    g = np.asarray(grad)
+    assert np.allclose(g, rgrad, rtol=1e-4, atol=1e-5 * np.abs(rgrad).max())
+
+
+def test_step_matches_oracle_eager_graph_and_host():
+    bt = _batch()
+    ref = _oracle(bt)
+    dev = torch.device('cuda:0')
+    t = {k: torch.from_numpy(v).to(dev) for k, v in bt.items()}
+    step = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
+    args = (t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
+    step.run(*args)
+    torch.cuda.synchronize()
+    _check(step, step.bits.cpu(), step.loss_sum.item(), step.grad_boxes.cpu(), ref)
+    # CUDA graph: capture once, replay twice on scrubbed outputs
+    step.capture(*args)
+    for _ in range(2):
+        step.bits.fill_(-1); step.grad_boxes.zero_(); step.loss_sum.zero_()
+        step.replay()
+        torch.cuda.synchronize()
+        _check(step, step.bits.cpu(), step.loss_sum.item(), step.grad_boxes.cpu(), ref)
+    # host buffers in, host results out
+    hin = {k: torch.from_numpy(v).pin_memory() for k, v in bt.items()}
+    hs = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
+    for _ in range(2):
+        bits, loss_sum, grad = hs.run_host(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'],
+                                           hin['weight'], float(F * M))
+        assert not bits.is_cuda and not grad.is_cuda
+        _check(hs, bits, loss_sum, grad, ref)
+    h2d, d2h = hs.host_bytes(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'])
+    assert h2d == sum(v.nbytes for v in bt.values()) and d2h == F * N * step.W * 4 + F * M * 7 * 4 + 4
+
+
+def test_workspace_contract_unzeroed_and_shared_sizes():
+    """A workspace that was never zeroed must still give exact results (the id-pool cursor
+    then overflows into the 'every box' fallback) and leaves itself clean for the next call."""
+    f = synth.make_frame(3, 2, N=4000)                       # dense SUN-RGBD-like scene, 512 boxes
+    ref = om.points_in_boxes_all_np(f['points'], f['boxes'], 8)
+    P, B = torch.from_numpy(f['points']).cuda()[None], torch.from_numpy(f['boxes']).cuda()[None]
+    L = G._lib.load()
+    nbytes = int(L.gga_pib_workspace_bytes(1, 4000, 512))
+    ws = torch.full((nbytes,), 0xAB, dtype=torch.uint8, device='cuda')
+    out = torch.empty((1, 4000, G.row_words(512)), dtype=torch.int32, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        out.fill_(-1)
+        G._lib.check(L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512,
+                                                ws.data_ptr(), ws.numel(), st))
+        assert np.array_equal(G.unpack_bits(out, 512)[0].cpu().numpy(), ref)
+    # too small / misaligned workspaces are rejected, not overrun
+    assert L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512,
+                                      ws.data_ptr(), 1024, st) == -1
+    assert L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512,
+                                      ws.data_ptr() + 4, ws.numel() - 4, st) == -1
+
+
+@pytest.mark.parametrize('T,N,B', [(1, 777, 1), (33, 1000, 2), (1500, 3000, 1), (5000, 1200, 1), (16, 300, 200)])
+def test_shapes_beyond_the_training_one(T, N, B):
+    """One box, rows wider than 32 words (T > 1024: fewer points per batch), more frames than SMs."""
+    rng = np.random.default_rng(T * 7 + N)
+    boxes = np.stack([synth.make_boxes(rng, T, 'sunrgbd' if T > 1000 else 'kitti') for _ in range(B)])
+    pts = np.stack([synth.make_points(rng, N, boxes[b], 'sunrgbd' if T > 1000 else 'kitti') for b in range(B)])
+    ref = np.stack([om.points_in_boxes_all_np(pts[b], boxes[b], 8) for b in range(B)])
+    P, Bx = torch.from_numpy(pts).cuda(), torch.from_numpy(boxes).cuda()
+    assert np.array_equal(G.unpack_bits(G.points_in_boxes_bits(P, Bx), T).cpu().numpy(), ref)
+    assert np.array_equal(G.points_in_boxes_all(P[..., :3], Bx).cpu().numpy(), ref)
+    part = G.points_in_boxes_part(P[..., :3], Bx).cpu().numpy()
+    assert np.array_equal(part, np.where(ref.any(2), ref.argmax(2), -1))

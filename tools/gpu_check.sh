@@ -1,19 +1,19 @@
 #!/bin/bash
 # One GPU session: parity tests, smoke, bench (both arms), ncu launch list + full capture of the
-# dominant kernel.  Outputs land in gpurun_out/ (merged back by gpurun).
+# membership kernels.  Outputs land in gpurun_out/ (merged back by gpurun).
 set -u
 TAG=${1:-r1}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
-python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" 
+python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/${TAG}_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
-python bench.py --steps 2000 --warmup 20 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
-cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err; echo "ref rc=$?"
 cat gpurun_out/${TAG}_bench_ref.json
+python bench.py --steps 2000 --warmup 20 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:pib -s 6 -c 2 -f -o gpurun_out/${TAG}_prof_pib \
+ncu --set full --clock-control none --import-source on -k regex:pib -s 12 -c 4 -f -o gpurun_out/${TAG}_prof_pib \
     python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
-ls -la gpurun_out | tail -20
+ls -la gpurun_out | grep ${TAG}
