@@ -9,8 +9,8 @@ Workload (BASELINE.json configs[1], "GGA KITTI training shape"): 8 frames per GP
 consistency loss against 2D targets, forward + backward to the box parameters.  Synthetic
 data (gga_b200/synth.py).  One "step" = one pass of the hot path over one
 batch of 8 frames.  Frames shard across ranks with no data-path collective ("weak" scaling);
-the only exchange is the scalar all-reduce of the loss sum (the reference's reduce_mean /
-_parse_losses), issued asynchronously.
+the only exchange is the scalar all-reduce of the accumulated loss sum at the log interval (the
+reference's reduce_mean / _parse_losses + TextLoggerHook interval=50), issued asynchronously.
 
 Prints ONE JSON line (rank 0).  Keys: see DESIGN.md §6.
 """
@@ -212,7 +212,8 @@ def run_ours(args):
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        import datetime
+        dist.init_process_group('nccl', device_id=dev, timeout=datetime.timedelta(seconds=180))
     import gga_b200 as G
     from gga_b200 import synth
     from gga_b200.step import GeometryStep
@@ -225,57 +226,81 @@ def run_ours(args):
     # synthetic frames: 2 distinct host batches per rank, replicated into n_sets device sets
     host = [synth.make_batch(CFG, 100000 * rank + 16 * k, F) for k in range(2)]
     sets, steps = [], []
+    # loss scalars: every step adds its weighted loss sum to a device accumulator (inside the loss
+    # kernel); the accumulator is all-reduced across ranks at the log interval, asynchronously on a
+    # side stream (the reference: mmdet reduce_mean / _parse_losses feeding a TextLoggerHook with
+    # interval=50, configs/gga/gga_kitti_config.py:251-254).  No collective sits on the data path.
+    acc = torch.zeros((4,), dtype=torch.float32, device=dev)
+    snaps = torch.zeros((64, 4), dtype=torch.float32, device=dev)
+    comm = torch.cuda.Stream() if world > 1 else None
+    works = []
+    if world > 1:   # create the NCCL communicator up front
+        dist.all_reduce(snaps[0])
+        torch.cuda.synchronize()
+
+    def reduce_scalars_async():
+        ev = torch.cuda.Event()
+        ev.record()
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            j = len(works) % 64
+            snaps[j].copy_(acc)
+            works.append(dist.all_reduce(snaps[j], async_op=True))
+
     for k in range(n_sets):
         hb = host[k % 2]
         t = {name: torch.from_numpy(np.ascontiguousarray(hb[name])).to(dev)
              for name in ('points', 'boxes', 'lidar2img', 'target', 'weight')}
         sets.append(t)
         s = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
+        s.loss_accum = acc[0:1]
         s.capture(t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
         steps.append(s)
     torch.cuda.synchronize()
+    # one graph holding a whole rotation of the buffer sets (amortises the graph launch), used for
+    # full rotations; the per-set graphs serve the remainder so that EXACTLY --steps steps are timed
+    rot = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(rot):
+        for k in range(n_sets):
+            t = sets[k]
+            steps[k].run(t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
+    torch.cuda.synchronize()
 
-    comm = torch.cuda.Stream() if world > 1 else None
-    red = torch.zeros((n_sets, 1), dtype=torch.float32, device=dev)
-    pending = []
+    log_rotations = max(1, round(50 / n_sets))   # ~ every 50 steps
 
-    def one_step(i):
-        s = steps[i % n_sets]
-        s.replay()
-        if world > 1:   # loss scalar all-reduce (reduce_mean / _parse_losses), off the critical path
-            ev = torch.cuda.Event()
-            ev.record()
-            comm.wait_event(ev)
-            with torch.cuda.stream(comm):
-                red[i % n_sets].copy_(s.loss_sum)
-                pending.append(dist.all_reduce(red[i % n_sets], async_op=True))
-            if len(pending) > 64:
-                pending.pop(0).wait()
+    def run_steps(n):
+        full, rem = divmod(n, n_sets)
+        for i in range(full):
+            rot.replay()
+            if world > 1 and (i + 1) % log_rotations == 0:
+                reduce_scalars_async()
+        for k in range(rem):
+            steps[k].replay()
+        if world > 1:
+            reduce_scalars_async()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        one_step(i)
+    run_steps(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        one_step(i)
+    run_steps(args.steps)
     e1.record()
     sampler.sample()
     if comm is not None:
         torch.cuda.current_stream().wait_stream(comm)
     barrier()
     sampler.stop()
+    for wk in works:
+        wk.wait()
     ms = e0.elapsed_time(e1)
     if world > 1:
-        for p in pending:
-            p.wait()
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
@@ -284,24 +309,30 @@ def run_ours(args):
 
     # dominant kernel alone (membership), same rotation of buffers, CUDA events on the launch stream
     L = G._lib.load()
-    st = torch.cuda.current_stream().cuda_stream
-    kreps = max(50, min(args.steps, 500))
 
     def member(i):
         t, s = sets[i % n_sets], steps[i % n_sets]
+        st = torch.cuda.current_stream().cuda_stream
         rc = L.gga_points_in_boxes_bits(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), s.bits.data_ptr(), F, N, M,
                                         s.ws.data_ptr(), s.ws.numel(), st)
         assert rc == 0
-    for i in range(5):
+    for i in range(n_sets):
         member(i)
     torch.cuda.synchronize()
+    mg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(mg):       # one rotation of membership launches, replayed by the driver
+        for i in range(n_sets):
+            member(i)
+    mg.replay()
+    torch.cuda.synchronize()
+    kreps = max(8, min(args.steps, 500) // n_sets)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for i in range(kreps):
-        member(i)
+        mg.replay()
     k1.record()
     torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / kreps
+    kernel_ms = k0.elapsed_time(k1) / (kreps * n_sets)
     peak, peak_src = peaks()
     achieved = member_bytes / (kernel_ms * 1e-3) / 1e9
 
@@ -337,7 +368,7 @@ def run_ours(args):
     if rank == 0:
         cfg = workload_config(c, world)
         cfg['l2'] = f'rotating {n_sets} input/output sets ({n_sets * all_bytes / 1e6:.0f} MB > 2x 126 MB L2)'
-        cfg['launch'] = 'CUDA graph replay per step'
+        cfg['launch'] = f'CUDA graphs: one per rotation of {n_sets} steps + one per step for the remainder'
         out = {
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_per_step, 5), 'higher_is_better': True,

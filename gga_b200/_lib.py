@@ -27,7 +27,7 @@ class BoxLossArgs(ctypes.Structure):
         ('n', c_int), ('mode', c_int), ('loss_kind', c_int), ('clamp_to_image', c_int),
         ('depth_clamp', ctypes.c_float), ('eps', ctypes.c_float), ('grad_scale', ctypes.c_float),
         ('box2d', c_void_p), ('valid', c_void_p), ('argidx', c_void_p), ('loss', c_void_p),
-        ('loss_sum', c_void_p), ('grad_boxes', c_void_p), ('grad_box2d', c_void_p),
+        ('loss_sum', c_void_p), ('loss_accum', c_void_p), ('grad_boxes', c_void_p), ('grad_box2d', c_void_p),
         ('grad_target', c_void_p),
     ]
 

@@ -42,6 +42,7 @@ class GeometryStep:
         self.box2d = torch.empty((n, 4), dtype=torch.float32, device=dev)
         self.loss = torch.empty((n, 4 if self.kind == _lib.LOSS_L1 else 1), dtype=torch.float32, device=dev)
         self.loss_sum = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self.loss_accum = None   # optional [1] running total shared by several steps (set by the caller)
         self.grad_boxes = torch.empty((n, 7), dtype=torch.float32, device=dev)
         self.ws = torch.zeros((int(L.gga_pib_workspace_bytes(self.F, self.N, self.M)),), dtype=torch.uint8,
                               device=dev)
@@ -50,12 +51,15 @@ class GeometryStep:
         self._host = None
 
     # ------------------------------------------------------------------ device-resident step
-    def run(self, points, boxes, lidar2img, target, weight=None, avg_factor=None):
+    def run(self, points, boxes, lidar2img, target, weight=None, avg_factor=None, after_loss=None):
         """points [F,N,pts_stride], boxes [F,M,7], lidar2img [F,M,4,4] (one calib per object,
         the GGA_lidar2img layout) or [4,4], target [F,M,4], weight [F,M] — contiguous fp32 CUDA
         tensors.  Enqueues the step on the current stream; returns nothing (results are in
         ``self.bits / box2d / loss / loss_sum / grad_boxes``; ``loss_sum`` is the weighted SUM,
-        gradients are already scaled by ``loss_weight / avg_factor``)."""
+        gradients are already scaled by ``loss_weight / avg_factor``).  ``after_loss`` (optional
+        callable) runs on the side stream right after the loss kernel — the place for the scalar
+        all-reduce of the loss sum (``gga_b200.dist.reduce_scalars``), which then overlaps the
+        membership kernels and is captured with them in the CUDA graph."""
         L = self.L
         n = self.F * self.M
         cur = torch.cuda.current_stream(self.device)
@@ -69,6 +73,9 @@ class GeometryStep:
                    'points_in_boxes_bits')
         a = self._box_args(boxes, lidar2img, target, weight, avg_factor)
         _lib.check(L.gga_box_project_loss(a, self.side.cuda_stream), 'box_project_loss')
+        if after_loss is not None:
+            with torch.cuda.stream(self.side):
+                after_loss(self)
         join = torch.cuda.Event()
         join.record(self.side)
         cur.wait_event(join)
@@ -106,6 +113,8 @@ class GeometryStep:
         a.grad_scale = self.loss_weight / float(avg_factor if avg_factor is not None else max(n, 1))
         a.box2d, a.loss, a.loss_sum = self.box2d.data_ptr(), self.loss.data_ptr(), self.loss_sum.data_ptr()
         a.grad_boxes = self.grad_boxes.data_ptr()
+        if self.loss_accum is not None:
+            a.loss_accum = self.loss_accum.data_ptr()
         return a
 
     def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3):

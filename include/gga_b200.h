@@ -149,6 +149,8 @@ typedef struct gga_box_loss_args {
   uint8_t* argidx;         /* [n, 4] corner index attaining (xmin, ymin, xmax, ymax), first wins */
   float* loss;             /* [n] unweighted per-box loss (L1: [n, 4] per side) */
   float* loss_sum;         /* [1]  sum_i w_i * loss_i  (deterministic order) */
+  float* loss_accum;       /* optional [1]: += the same sum (running total over steps, reduced across ranks
+                              at the log interval: gga_kitti_config.py:251-254) */
   float* grad_boxes;       /* [n, 7] d(total)/d(boxes) */
   float* grad_box2d;       /* [n, 4] d(total)/d(box2d) */
   float* grad_target;      /* [n, 4] d(total)/d(target) (PGD passes a prediction as target) */
