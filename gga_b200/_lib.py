@@ -7,7 +7,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, '_C', 'libgga_b200.so')
+_LIB_PATH = os.environ.get('GGA_B200_LIB') or os.path.join(_HERE, '_C', 'libgga_b200.so')  # env: A/B testing of builds
 _lock = threading.Lock()
 _lib = None
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     'gga_image_box_overlap_f64': ([c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
     'gga_test_pib_phase': ([c_int], c_int),
     'gga_test_pib_trace': ([c_void_p], c_int),
+    'gga_test_pib_trace_prep': ([c_void_p], c_int),
     'gga_test_sincos': ([c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p], c_int),
     'gga_test_box_prep': ([c_void_p, c_int, c_void_p, c_void_p], c_int),
 }
@@ -83,6 +84,8 @@ def load():
             _build.build()
         L = ctypes.CDLL(_LIB_PATH)
         for name, (argtypes, restype) in SIGNATURES.items():
+            if name.startswith('gga_test_') and not hasattr(L, name):
+                continue  # profiling / test hooks are optional (A/B runs against older builds)
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.argtypes = argtypes
             fn.restype = restype

@@ -31,9 +31,15 @@
 
 namespace {
 
-constexpr int kStreamThreads = 256;
+#ifndef GGA_STREAM_THREADS
+#define GGA_STREAM_THREADS 256
+#endif
+#ifndef GGA_OCC
+#define GGA_OCC 5
+#endif
+constexpr int kStreamThreads = GGA_STREAM_THREADS;
 constexpr int kWarps = kStreamThreads / 32;
-constexpr int kOcc = 5;  // stream CTAs per SM (48 registers per thread)
+constexpr int kOcc = GGA_OCC;  // stream CTAs per SM (5 x 256 threads: 48 registers per thread)
 constexpr int kPrepThreads = 512;
 constexpr int kMaxRanges = 1024;
 constexpr int kMaxSliceCells = 4096;
@@ -167,13 +173,12 @@ __device__ __forceinline__ int pcell(float v, float g0, float inv, float gp1) {
 }
 
 // Workspace layout (device memory owned by the caller, see gga_pib_workspace_bytes):
-//   uint32   ids_used[F]        allocation cursor of every frame's id pool; zero between calls
 //   FrameHdr hdr[F]
 //   float4   prep[F][2 T]       box t: [2t] = (cx, cy, cz, hz), [2t+1] = (cosa, sina, hx, hy)
 //   uint32   grid[F][gstride]   cell words, row-major (G + 2) x (G + 2) of the frame's own G
-//   uint16   ids[F][cap]
+//   uint16   ids[F][cap]        every slice of the prep grid owns cap / S entries
 struct WsLayout {
-  size_t ids_used, hdr, prep, grid, ids, total;
+  size_t hdr, prep, grid, ids, total;
   size_t gstride;  // words per frame
   uint32_t cap;    // ids per frame
   int Gmax;
@@ -191,7 +196,6 @@ inline WsLayout ws_layout(int F, int T, int Gmax) {
   cap = cap & ~(size_t)7;
   L.cap = (uint32_t)cap;
   size_t o = 0;
-  L.ids_used = o; o = align_up(o + (size_t)F * 4, 256);
   L.hdr = o; o = align_up(o + (size_t)F * sizeof(FrameHdr), 256);
   L.prep = o; o = align_up(o + (size_t)F * T * 32, 256);
   L.grid = o; o = align_up(o + (size_t)F * L.gstride * 4, 256);
@@ -200,8 +204,9 @@ inline WsLayout ws_layout(int F, int T, int Gmax) {
   return L;
 }
 
-int g_tune_grid = 0, g_tune_occ = 0, g_tune_dynamic = 0, g_tune_phase = 0;
+int g_tune_grid = 0, g_tune_occ = 0, g_tune_phase = 0, g_tune_nogsm = 0, g_tune_nofast = 0, g_tune_gsm = 0;
 unsigned long long* g_trace = nullptr;
+unsigned long long* g_trace_prep = nullptr;
 
 inline int pick_gmax(int N, int T) {
   if (g_tune_grid > 0) return g_tune_grid > kMaxG ? kMaxG : g_tune_grid;
@@ -222,6 +227,10 @@ struct PrepParams {
   WsLayout L;
   int T;
   int ncache;  // boxes whose raster terms are cached in shared memory
+  int Gcap;             // largest G whose slices fit the shared-memory cell arrays
+  int S;                // index slices per frame (grid.x = S + CTAs for the exact contract terms)
+  int max_slice_cells;  // cells of a slice at G = Gcap
+  unsigned long long* trace;  // profiling hook: 16 globaltimer stamps per CTA (NULL = off)
 };
 
 __device__ __forceinline__ void cell_range(const RasterBox& rb, const FrameHdr& h, int& cx0, int& cx1, int& cy0,
@@ -264,27 +273,49 @@ __device__ __forceinline__ bool sat_overlap(const SatBox& s, const FrameHdr& h, 
 __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams p) {
   // let the dependent stream kernel start its prologue right away
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  int tk = 0;
+  auto stamp = [&]() {
+    if (p.trace && threadIdx.x == 0 && tk < 16) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + tk] = t;
+    }
+    ++tk;
+  };
+  stamp();
   extern __shared__ __align__(16) unsigned char dsm[];
   constexpr int kCells = kMaxSliceCells + 4;
-  uint32_t* cf = reinterpret_cast<uint32_t*>(dsm);   // candidates per cell (count pass), then fill cursor << 16
-  uint32_t* word = cf + kCells;                      // inline ids 0,1 -> final cell word
-  uint32_t* word2 = word + kCells;                   // inline ids 2,3 -> list offset
-  uint16_t* mine = reinterpret_cast<uint16_t*>(word2 + kCells);  // [T] boxes touching this slice
-  float* cbox = reinterpret_cast<float*>(dsm + (size_t)3 * kCells * 4 + align_up((size_t)p.T * 2, 16));
+  uint32_t* cf = reinterpret_cast<uint32_t*>(dsm);   // candidates per cell (raster pass), then n | fill cursor << 16
+  uint32_t* word = cf + kCells;                      // inline ids 0,1
+  uint32_t* word2 = word + kCells;                   // inline ids 2,3 -> list offset of cells with > kInline boxes
+  uint32_t* mine = word2 + kCells;                   // [T] boxes touching this slice: id | cx0 << 16, then cx1 | cy0 << 8 ...
+  float* cbox = reinterpret_cast<float*>(dsm + (size_t)3 * kCells * 4 + align_up((size_t)p.T * 12, 16));
   constexpr int kNW = kPrepThreads / 32;
   __shared__ uint32_t s_minx, s_miny, s_maxx, s_maxy;
-  __shared__ int s_nrect, s_ninf, s_nmine, s_overflow;
+  __shared__ int s_nrect, s_ninf, s_nmine, s_big;
   __shared__ float s_sw[kNW], s_sh[kNW], s_swh[kNW];
-  __shared__ FrameHdr s_hdr;
-  __shared__ uint32_t s_base, s_warp_tot[kNW];
+  __shared__ uint32_t s_cursor;
 
   const int T = p.T, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int f = blockIdx.y, slice = blockIdx.x, S = gridDim.x;
+  const int f = blockIdx.y, slice = blockIdx.x, S = p.S;
   const float* __restrict__ boxes = p.boxes + (size_t)f * T * 7;
   unsigned char* ws = p.ws;
-  uint32_t* ids_used = reinterpret_cast<uint32_t*>(ws + p.L.ids_used) + f;
   float4* prep = reinterpret_cast<float4*>(ws + p.L.prep) + (size_t)f * 2 * T;
+  if (slice >= S) {
+    // CTAs beyond the S index slices: the exact (double precision) contract terms, one box per
+    // thread.  A ~3 us dependent chain (measured) that nothing in this kernel waits for.
+    const int t = (slice - S) * kPrepThreads + tid;
+    if (t < T) {
+      const BoxPrep q = prep_box(boxes + (size_t)t * 7);
+      prep[2 * t] = make_float4(q.cx, q.cy, q.cz, q.hz);
+      prep[2 * t + 1] = make_float4(q.cosa, q.sina, q.hx, q.hy);
+    }
+    return;
+  }
   uint32_t* grid = reinterpret_cast<uint32_t*>(ws + p.L.grid) + (size_t)f * p.L.gstride;
+  // this slice's own share of the frame's id pool (static split: no cursor, no zero-init contract)
+  const uint32_t pool = (p.L.cap / (uint32_t)S) & ~7u;
+  const uint32_t pool0 = (uint32_t)slice * pool;
   uint16_t* ids = reinterpret_cast<uint16_t*>(ws + p.L.ids) + (size_t)f * p.L.cap;
   const int ncache = p.ncache;
 
@@ -300,31 +331,29 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     return raster_box(boxes + (size_t)t * 7);
   };
 
+  // request this thread's first box before anything else: at the training shape the boxes come
+  // from DRAM behind the previous step's mask write-back (~2 us measured), the longest wait here
+  float b0[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) b0[j] = tid < T ? __ldg(boxes + (size_t)tid * 7 + j) : 0.f;
   if (tid == 0) {
     s_minx = s_miny = 0xffffffffu;
     s_maxx = s_maxy = 0u;
-    s_nrect = s_ninf = s_nmine = s_overflow = 0;
+    s_nrect = s_ninf = s_nmine = s_big = 0;
+    s_cursor = 0u;
   }
+  // cell arrays of the largest slice this launch can produce
+  for (int i = tid; i < p.max_slice_cells; i += kPrepThreads) { cf[i] = 0u; word[i] = 0u; word2[i] = 0u; }
   __syncthreads();
+  stamp();
 
-  // ---- pass A (all warps but the last): footprints, their extent, and the sums that predict
-  //      the list length; the last warp meanwhile evaluates the exact contract terms of this
-  //      slice's share of the boxes ------------------------------------------------------------
-  if (warp == kNW - 1) {
-    const int per = (T + S - 1) / S;
-    const int t0 = min(T, slice * per), t1 = min(T, t0 + per);
-    for (int t = t0 + lane; t < t1; t += 32) {
-      const BoxPrep q = prep_box(boxes + (size_t)t * 7);
-      prep[2 * t] = make_float4(q.cx, q.cy, q.cz, q.hz);
-      prep[2 * t + 1] = make_float4(q.cosa, q.sina, q.hx, q.hy);
-    }
-    if (lane == 0) s_sw[warp] = s_sh[warp] = s_swh[warp] = 0.f;
-  } else {
+  // ---- pass A: footprints, their extent, and the sums that predict the list length ---------
+  {
     float sw = 0.f, sh = 0.f, swh = 0.f;
     uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mxx = 0u, mxy = 0u;
     int nrect = 0, ninf = 0;
-    for (int t = tid; t < T; t += kPrepThreads - 32) {
-      const RasterBox rb = raster_box(boxes + (size_t)t * 7);
+    for (int t = tid; t < T; t += kPrepThreads) {
+      const RasterBox rb = t == tid ? raster_box(b0) : raster_box(boxes + (size_t)t * 7);
       if (t < ncache) {
         float* c = cbox + t * kBoxWords;
         c[0] = rb.x0; c[1] = rb.x1; c[2] = rb.y0; c[3] = rb.y1;
@@ -345,12 +374,6 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
     mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
     nrect = __reduce_add_sync(0xffffffffu, nrect); ninf = __reduce_add_sync(0xffffffffu, ninf);
-    if (lane == 0) {
-      atomicMin(&s_minx, mnx); atomicMax(&s_maxx, mxx);
-      atomicMin(&s_miny, mny); atomicMax(&s_maxy, mxy);
-      if (nrect) atomicAdd(&s_nrect, nrect);
-      if (ninf) atomicAdd(&s_ninf, ninf);
-    }
     // fixed reduction tree: every slice of the frame computes bit-identical sums
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -358,15 +381,32 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
       sh += __shfl_xor_sync(0xffffffffu, sh, o);
       swh += __shfl_xor_sync(0xffffffffu, swh, o);
     }
-    if (lane == 0) { s_sw[warp] = sw; s_sh[warp] = sh; s_swh[warp] = swh; }
+    if (lane == 0) {
+      atomicMin(&s_minx, mnx); atomicMax(&s_maxx, mxx);
+      atomicMin(&s_miny, mny); atomicMax(&s_maxy, mxy);
+      if (nrect) atomicAdd(&s_nrect, nrect);
+      if (ninf) atomicAdd(&s_ninf, ninf);
+      s_sw[warp] = sw; s_sh[warp] = sh; s_swh[warp] = swh;
+    }
   }
   __syncthreads();
-  if (tid == 0) {
-    FrameHdr h;
-    h.n_rect = s_nrect; h.n_inf = s_ninf; h.pad = 0;
+  stamp();
+  // ---- header: every thread computes it redundantly from the block-wide results (same code,
+  //      same inputs, same bits) — cheaper than one thread computing and a barrier publishing ----
+  FrameHdr h;
+  {
+    float sw = lane < kNW ? s_sw[lane] : 0.f, sh = lane < kNW ? s_sh[lane] : 0.f, swh = lane < kNW ? s_swh[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sw += __shfl_xor_sync(0xffffffffu, sw, o);
+      sh += __shfl_xor_sync(0xffffffffu, sh, o);
+      swh += __shfl_xor_sync(0xffffffffu, swh, o);
+    }
+    const int nrect = s_nrect, ninf = s_ninf;
+    h.n_rect = nrect; h.n_inf = ninf; h.pad = 0;
     float gx0 = 0.f, gy0 = 0.f, gx1 = 0.f, gy1 = 0.f, wx = 0.f, wy = 0.f;
     bool degenerate = true;  // no finite footprint, or extents overflow fp32: one inner cell
-    if (s_nrect > 0) {
+    if (nrect > 0) {
       gx0 = ord2f(s_minx); gy0 = ord2f(s_miny);
       gx1 = ord2f(s_maxx); gy1 = ord2f(s_maxy);
       wx = gx1 - gx0;
@@ -374,60 +414,60 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
       degenerate = !isfinite(wx) || !isfinite(wy);
     }
     int G = 1;
+    float invx = 0.f, invy = 0.f, cwx = INFINITY, cwy = INFINITY;
     if (!degenerate) {
-      float sw = 0.f, sh = 0.f, swh = 0.f;
-      for (int w = 0; w < kNW; ++w) { sw += s_sw[w]; sh += s_sh[w]; swh += s_swh[w]; }
       // entries(G) ~ sum over boxes of (w G / Lx + 2)(h G / Ly + 2), + (G + 2)^2 per unbounded box
-      const float ax = wx > 0.f ? sw / wx : (float)s_nrect, ay = wy > 0.f ? sh / wy : (float)s_nrect;
-      const float axy = (wx > 0.f && wy > 0.f) ? swh / (wx * wy) : (float)s_nrect;
-      const float budget = 0.75f * (float)p.L.cap;
-      G = p.L.Gmax;
+      const float rx = wx > 0.f ? __frcp_rn(wx) : 0.f, ry = wy > 0.f ? __frcp_rn(wy) : 0.f;
+      const float ax = wx > 0.f ? sw * rx : (float)nrect, ay = wy > 0.f ? sh * ry : (float)nrect;
+      const float axy = (wx > 0.f && wy > 0.f) ? swh * rx * ry : (float)nrect;
+      const float budget = 0.5f * (float)p.L.cap;  // half: the pool is split statically between the slices
+      G = p.Gcap;                                  // largest G whose slices fit the shared-memory cell arrays
       while (G > 1) {
         const float g = (float)G;
-        const float e = axy * g * g + 2.f * (ax + ay) * g + 4.f * (float)s_nrect +
-                        (float)s_ninf * (g + 2.f) * (g + 2.f);
-        const int rps = (G + 2 + S - 1) / S;
-        if (e <= budget && rps * (G + 2) <= kMaxSliceCells) break;  // (NaN e: keep shrinking)
+        const float e = axy * g * g + 2.f * (ax + ay) * g + 4.f * (float)nrect + (float)ninf * (g + 2.f) * (g + 2.f);
+        if (e <= budget) break;  // (NaN e: keep shrinking)
         G = G * 7 / 8;
         if (G < 1) G = 1;
       }
+      // any positive scale works (points and footprints share it); the reciprocal of the
+      // estimate above is reused, its 1-ulp error is inside the cell slack of the SAT test
+      invx = (float)G * rx;
+      invy = (float)G * ry;
+      if (!isfinite(invx)) invx = 0.f;
+      if (!isfinite(invy)) invy = 0.f;
+      const float rg = __frcp_rn((float)G);
+      if (invx > 0.f) cwx = wx * rg;
+      if (invy > 0.f) cwy = wy * rg;
     } else {
-      gx0 = gy0 = gx1 = gy1 = wx = wy = 0.f;
+      gx0 = gy0 = gx1 = gy1 = 0.f;
     }
     h.G = G;
     h.gx0 = gx0; h.gy0 = gy0;
-    float invx = 0.f, invy = 0.f, cwx = INFINITY, cwy = INFINITY;
-    if (!degenerate) {
-      invx = (wx > 0.f) ? (float)G / wx : 0.f;
-      invy = (wy > 0.f) ? (float)G / wy : 0.f;
-      if (!isfinite(invx)) invx = 0.f;
-      if (!isfinite(invy)) invy = 0.f;
-      if (invx > 0.f) cwx = wx / (float)G;
-      if (invy > 0.f) cwy = wy / (float)G;
-    }
     h.invx = invx; h.invy = invy; h.cwx = cwx; h.cwy = cwy;
     h.slopx = (fabsf(gx0) + fabsf(gx1)) * 3.814697265625e-6f;  // 2^-18
     h.slopy = (fabsf(gy0) + fabsf(gy1)) * 3.814697265625e-6f;
-    s_hdr = h;
   }
-  __syncthreads();
-  const FrameHdr h = s_hdr;
   const int G = h.G, Gp = G + 2;
   const int rps = (Gp + S - 1) / S;
   const int row0 = min(Gp, slice * rps), row1 = min(Gp, row0 + rps);
-  const int ncell = (row1 - row0) * Gp;  // cells of this slice
+  const int ncell = (row1 - row0) * Gp;  // cells of this slice (<= p.max_slice_cells)
   if (slice == 0 && tid == 0) reinterpret_cast<FrameHdr*>(ws + p.L.hdr)[f] = h;
 
-  // ---- pass C: boxes touching this slice --------------------------------------------------
-  for (int i = tid; i < ncell; i += kPrepThreads) { cf[i] = 0u; word[i] = 0u; word2[i] = 0u; }
+  // ---- pass C: boxes touching this slice, with their cell ranges --------------------------
   for (int t = tid; t < T; t += kPrepThreads) {
     const RasterBox rb = get_box(t);
     if (rb.kind == 0) continue;
     int cx0, cx1, cy0, cy1;
     cell_range(rb, h, cx0, cx1, cy0, cy1);
-    if (cy1 >= row0 && cy0 < row1) mine[atomicAdd(&s_nmine, 1)] = (uint16_t)t;
+    if (cy1 >= row0 && cy0 < row1) {
+      const int k = atomicAdd(&s_nmine, 1);
+      mine[3 * k] = (uint32_t)t;
+      mine[3 * k + 1] = (uint32_t)cx0 | ((uint32_t)cx1 << 16);
+      mine[3 * k + 2] = (uint32_t)max(cy0, row0) | ((uint32_t)min(cy1, row1 - 1) << 16);
+    }
   }
   __syncthreads();
+  stamp();
   const int nmine = s_nmine;
 
   // Visits every (box, local cell) incidence of this slice; a half warp per box, its 16
@@ -436,12 +476,11 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
   auto raster = [&](auto visit) {
     const int hw = tid >> 4, l16 = tid & 15, xx = l16 & 3, yy = l16 >> 2;
     for (int i = hw; i < nmine; i += kPrepThreads / 16) {
-      const int t = mine[i];
+      const int t = (int)mine[3 * i];
+      const uint32_t rx = mine[3 * i + 1], ry = mine[3 * i + 2];
+      const int cx0 = (int)(rx & 0xffffu), cx1 = (int)(rx >> 16), y0 = (int)(ry & 0xffffu), y1 = (int)(ry >> 16);
       const RasterBox rb = get_box(t);
       const SatBox sb = sat_box(rb, h);
-      int cx0, cx1, cy0, cy1;
-      cell_range(rb, h, cx0, cx1, cy0, cy1);
-      const int y0 = max(cy0, row0), y1 = min(cy1, row1 - 1);
       for (int ty = y0 + yy; ty <= y1; ty += 4)
         for (int tx = cx0 + xx; tx <= cx1; tx += 4) {
           const bool border = (tx == 0) | (tx == G + 1) | (ty == 0) | (ty == G + 1);
@@ -455,79 +494,48 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
     const uint32_t k = atomicAdd(&cf[c], 1u);
     if (k < 2u) atomicOr(&word[c], (uint32_t)t << (15u * k));
     else if (k < (uint32_t)kInline) atomicOr(&word2[c], (uint32_t)t << (15u * (k - 2u)));
+    else if (k == (uint32_t)kInline) s_big = 1;
   });
   __syncthreads();
+  stamp();
 
-  // ---- scan: list space of the cells with >= 3 candidates ----------------------------------
-  const int cpt = (ncell + kPrepThreads - 1) / kPrepThreads;
-  const int c0 = min(ncell, tid * cpt), c1 = min(ncell, c0 + cpt);
-  uint32_t need = 0;
-  bool big = false;
-  for (int c = c0; c < c1; ++c) {
+  // ---- emit: final cell words straight to the grid; list space from a slice-local cursor ---
+  const bool any_big = s_big != 0;
+  for (int c = tid; c < ncell; c += kPrepThreads) {
     const uint32_t n = cf[c];
-    if (n >= 3u) need += n + (n >= kCntLong ? 1u : 0u);
-    big |= n > (uint32_t)kInline;
-  }
-  uint32_t incl = need;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp_tot[warp] = incl;
-  const int any_big = __syncthreads_or(big ? 1 : 0);
-  if (tid == 0) {
-    uint32_t run = 0;
-    for (int w = 0; w < kNW; ++w) {
-      const uint32_t v = s_warp_tot[w];
-      s_warp_tot[w] = run;
-      run += v;
-    }
-    uint32_t base = 0;
-    if (run > 0) {
-      base = atomicAdd(ids_used, run);
-      if ((unsigned long long)base + run > (unsigned long long)p.L.cap) s_overflow = 1;
-    }
-    s_base = base;
-  }
-  __syncthreads();
-  const bool overflow = s_overflow != 0;
-  {
-    // final words; lists of <= kInline candidates are written straight from the inline slots
-    uint32_t off = s_base + s_warp_tot[warp] + (incl - need);
-    for (int c = c0; c < c1; ++c) {
-      const uint32_t n = cf[c];
-      const uint32_t w01 = word[c], w23 = word2[c];
-      uint32_t w = 0u;
-      if (n == 1u) {
-        w = (1u << kKindShift) | (w01 & kIdMask);
-      } else if (n == 2u) {
-        w = (2u << kKindShift) | (w01 & 0x3fffffffu);
-      } else if (n >= 3u) {
-        if (overflow) {
-          w = kCellAll;
+    const uint32_t w01 = word[c], w23 = word2[c];
+    uint32_t w = 0u;
+    if (n == 1u) {
+      w = (1u << kKindShift) | (w01 & kIdMask);
+    } else if (n == 2u) {
+      w = (2u << kKindShift) | (w01 & 0x3fffffffu);
+    } else if (n >= 3u) {
+      const bool lng = n >= kCntLong;
+      const uint32_t need = n + (lng ? 1u : 0u);
+      const uint32_t off = atomicAdd(&s_cursor, need);
+      if (off + need > pool) {
+        w = kCellAll;  // this slice's share of the pool is exhausted: test every box (slow, exact)
+        cf[c] = 0u;
+      } else {
+        const uint32_t o = pool0 + off;
+        w = (3u << kKindShift) | ((lng ? kCntLong : n) << kListCntShift) | o;
+        if (n <= (uint32_t)kInline) {
+          ids[o] = (uint16_t)(w01 & kIdMask);
+          ids[o + 1] = (uint16_t)((w01 >> 15) & kIdMask);
+          ids[o + 2] = (uint16_t)(w23 & kIdMask);
+          if (n == 4u) ids[o + 3] = (uint16_t)((w23 >> 15) & kIdMask);
         } else {
-          const bool lng = n >= kCntLong;
-          w = (3u << kKindShift) | ((lng ? kCntLong : n) << kListCntShift) | off;
-          if (n <= (uint32_t)kInline) {
-            ids[off] = (uint16_t)(w01 & kIdMask);
-            ids[off + 1] = (uint16_t)((w01 >> 15) & kIdMask);
-            ids[off + 2] = (uint16_t)(w23 & kIdMask);
-            if (n == 4u) ids[off + 3] = (uint16_t)((w23 >> 15) & kIdMask);
-          } else {
-            if (lng) ids[off] = (uint16_t)n;
-            word2[c] = off + (lng ? 1u : 0u);  // where the fill pass writes this cell's list
-            cf[c] = n;                         // fill cursor in the upper half starts at 0
-          }
-          off += n + (lng ? 1u : 0u);
+          if (lng) ids[o] = (uint16_t)n;
+          word2[c] = o + (lng ? 1u : 0u);  // where the fill pass writes this cell's list
         }
       }
-      word[c] = w;
     }
+    grid[row0 * Gp + c] = w;
   }
   // ---- fill pass, only when some cell of the slice holds more than kInline candidates ------
-  if (any_big && !overflow) {
+  if (any_big) {
     __syncthreads();
+    stamp();
     raster([&](int t, int c) {
       const uint32_t n = cf[c] & 0xffffu;
       if (n > (uint32_t)kInline) {
@@ -536,8 +544,7 @@ __global__ void __launch_bounds__(kPrepThreads) pib_prep_kernel(const PrepParams
       }
     });
   }
-  __syncthreads();
-  for (int c = tid; c < ncell; c += kPrepThreads) grid[row0 * Gp + c] = word[c];
+  stamp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -556,7 +563,8 @@ struct StreamParams {
   int slots;              // warps per range
   int vec4;
   int smem_prep;          // the CTA keeps the contract terms of one frame in shared memory
-  int dynamic;            // warps draw their batches from the per-range counter (else static strides)
+  int dynamic;            // CTA-local dynamic batch draws instead of static strides (experiment; default off)
+  int grid_smem_words;    // GSM variant: words of the frame's cell grid copied to shared memory
   unsigned long long* trace;  // profiling hook: 16 globaltimer stamps per warp (NULL = off)
 };
 
@@ -580,7 +588,7 @@ __device__ __forceinline__ float4 ld_f4(const float4* p) {
   return v;
 }
 
-__device__ __forceinline__ void trace_stamp(const StreamParams& p, int k) {
+__device__ __forceinline__ void trace_stamp(const StreamParams& p, int k, int kWarps = 8) {
   if (p.trace && (threadIdx.x & 31) == 0 && k < 15) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -669,26 +677,36 @@ __device__ __forceinline__ void for_each_hit(uint32_t w, const StreamParams& p, 
 // tail of slow warps, not bandwidth bound.
 // Software pipeline per warp: the points of batch n+2 are in flight, the cell word of batch
 // n+1 is requested, batch n is tested and written.
-template <int MODE, int WS, bool VEC4>
-__global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const StreamParams p) {
+// NT threads per CTA; GSM: one big CTA per SM that also keeps the cell grid of its frame in
+// shared memory — a warp-wide gather of 32 scattered cell words costs ~32 L1 wavefronts from
+// global memory but only a few bank-conflict replays from shared memory (the gathers were the
+// hidden limiter of the L1 variant: same 18 us at every occupancy / block size).
+template <int MODE, int WS, bool VEC4, int NT, bool GSM>
+__global__ void __launch_bounds__(NT, GSM ? 1 : kOcc) pib_stream_kernel(const StreamParams p) {
+  constexpr int kWarps = NT / 32;
+  constexpr int kStreamThreads = NT;
   extern __shared__ __align__(16) uint32_t smem_all[];
-  trace_stamp(p, 0);
+  trace_stamp(p, 0, kWarps);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = WS > 0 ? WS : p.row_words;
   const int P = (MODE == kModePart || WS > 0) ? 32 : p.batch_pts;
   const int N = p.num_points, bpf = p.batches_per_frame, slots = p.slots;
   const int stage_words = P * W;
   // shared memory: [contract terms of one frame: 2 T float4, when they fit][per-warp stages]
+  // [GSM: cell grid of one frame][contract terms of one frame][per-warp stages]
+  const int grid_words = GSM ? p.grid_smem_words : 0;
   const int prep_words = p.smem_prep ? 8 * p.num_boxes : 0;
-  const float4* prep_smem = reinterpret_cast<const float4*>(smem_all);
-  uint32_t* stage = smem_all + prep_words + (size_t)warp * stage_words;
+  const uint32_t* grid_smem = smem_all;
+  const float4* prep_smem = reinterpret_cast<const float4*>(smem_all + grid_words);
+  uint32_t* stage = smem_all + grid_words + prep_words + (size_t)warp * stage_words;
 
   const int r = blockIdx.x % p.R, slot = (int)(blockIdx.x / p.R) * kWarps + warp;
   const int nb = p.tb_base + (r < p.tb_rem ? 1 : 0);  // batches of this range
   const int g0 = r * p.tb_base + min(r, p.tb_rem);    // first batch of the range
   const int rf0 = g0 / bpf, rc0 = g0 - rf0 * bpf;     // its frame / batch inside the frame
   // the frame whose contract terms this CTA keeps in shared memory: that of its first batch
-  const int f_smem = p.smem_prep ? min(p.num_frames - 1, (g0 + (int)(blockIdx.x / p.R) * kWarps) / bpf) : -1;
+  const int f_cta = min(p.num_frames - 1, (g0 + (int)(blockIdx.x / p.R) * kWarps) / bpf);
+  const int f_smem = p.smem_prep ? f_cta : -1;
 
   struct Batch { int f, c; };  // frame, batch inside the frame; f < 0: none
   auto decode = [&](int b) -> Batch {  // b: batch index inside the range, or < 0
@@ -718,10 +736,10 @@ __global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const 
   float x = 0.f, y = 0.f, z = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
   fetch(cur, x, y, z);
 
-  trace_stamp(p, 1);
+  trace_stamp(p, 1, kWarps);
   // everything below reads what the prep kernel wrote
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  trace_stamp(p, 2);
+  trace_stamp(p, 2, kWarps);
   // batch draws: after its static batch a warp takes batches from its CTA's slab of the range
   // through a shared-memory counter (fast warps relieve slow ones; an L2 counter per range was
   // measured slower: 80 same-address atomics per range at kernel start cost ~5 us)
@@ -740,14 +758,15 @@ __global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const 
     return b < slab1 ? b : -1;
   };
   if (threadIdx.x == 0) s_draw = 0u;
-  if (blockIdx.x == 0 && threadIdx.x < 32) {  // hand the id-pool cursors back zeroed
-    uint32_t* used = reinterpret_cast<uint32_t*>(p.ws + p.L.ids_used);
-    for (int q = lane; q < p.num_frames; q += 32) used[q] = 0u;
-  }
   if (p.smem_prep) {
     const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f_smem * 2 * p.num_boxes;
-    float4* dst = reinterpret_cast<float4*>(smem_all);
+    float4* dst = reinterpret_cast<float4*>(smem_all + grid_words);
     for (int k = threadIdx.x; k < 2 * p.num_boxes; k += kStreamThreads) dst[k] = ld_f4(src + k);
+  }
+  if constexpr (GSM) {
+    const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.grid + (size_t)f_cta * p.L.gstride * 4);
+    float4* dst = reinterpret_cast<float4*>(smem_all);
+    for (int k = threadIdx.x; k < (grid_words >> 2); k += kStreamThreads) dst[k] = ld_f4(src + k);
   }
   __syncthreads();
 
@@ -756,12 +775,17 @@ __global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const 
   auto lookup = [&](const Batch& t, float lx, float ly) -> uint32_t {
     if (t.f < 0) return 0u;
     if (t.f != fc.f) fc = load_frame(p, t.f);
-    return (lane < P && t.c * P + lane < N) ? ld_u32(fc.grid + cell_of(lx, ly, fc)) : 0u;
+    if (lane >= P || t.c * P + lane >= N) return 0u;
+    const int cell = cell_of(lx, ly, fc);
+    if constexpr (GSM) {
+      if (t.f == f_cta) return grid_smem[cell];
+    }
+    return ld_u32(fc.grid + cell);
   };
   nxt = decode(cur.f >= 0 ? draw() : -1);
   fetch(nxt, x1, y1, z1);
   uint32_t wn = lookup(cur, x, y);
-  trace_stamp(p, 3);
+  trace_stamp(p, 3, kWarps);
   int tk = 4;
 
 #pragma unroll 1
@@ -833,9 +857,77 @@ __global__ void __launch_bounds__(kStreamThreads, kOcc) pib_stream_kernel(const 
       }
       __syncwarp();
     }
-    trace_stamp(p, tk++);
+    trace_stamp(p, tk++, kWarps);
   }
-  trace_stamp(p, 14);
+  trace_stamp(p, 14, kWarps);
+}
+
+// ------------------------------------------------------------------------------------------
+// stream kernel, lean variant for the training shapes: bit-packed rows of 8 words (129..256
+// boxes), 16-byte points, N a multiple of 32.  Then batch g of the frame-major list is simply
+// points[32 g .. 32 g + 31] and rows out[256 g ..], every batch is full and aligned, and the
+// per-batch bookkeeping of the general kernel (frame decode, partial batches, alignment and
+// tail paths: ~60 of its ~240 warp instructions per batch) disappears.  The SM is
+// instruction-issue bound in this kernel, so instructions are what is being saved.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, kOcc) pib_stream_fast_kernel(const StreamParams p) {
+  constexpr int W = 8, kW = 8;  // row words, warps per CTA
+  extern __shared__ __align__(16) uint32_t smem_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bpf = p.batches_per_frame, stride = p.slots, T = p.num_boxes;
+  const float4* prep_smem = reinterpret_cast<const float4*>(smem_all);
+  uint32_t* stage = smem_all + 8 * T + warp * (32 * W);
+
+  const int r = blockIdx.x % p.R, cta = (int)(blockIdx.x / p.R);
+  const int g0 = r * p.tb_base + min(r, p.tb_rem);
+  const int gend = g0 + p.tb_base + (r < p.tb_rem ? 1 : 0);
+  const int f_smem = min(p.num_frames - 1, (g0 + cta * kW) / bpf);  // frame whose contract terms sit in smem
+  int g = g0 + cta * kW + warp;                                     // this warp's batches: g, g + stride, ...
+  const float4* pts = reinterpret_cast<const float4*>(p.points) + lane;
+  float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+  if (g < gend) v0 = __ldcs(pts + (size_t)g * 32);
+  if (g + stride < gend) v1 = __ldcs(pts + (size_t)(g + stride) * 32);
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the prep kernel wrote
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f_smem * 2 * T;
+    float4* dst = reinterpret_cast<float4*>(smem_all);
+    for (int k = threadIdx.x; k < 2 * T; k += 256) dst[k] = ld_f4(src + k);
+  }
+  __syncthreads();
+  if (g >= gend) return;
+
+  int f = g / bpf, fend = (f + 1) * bpf;  // frame of the batch whose cell word is being requested
+  FrameCtx fc = load_frame(p, f);
+  uint32_t wn = ld_u32(fc.grid + cell_of(v0.x, v0.y, fc));
+#pragma unroll 1
+  for (;;) {
+    const float4 v = v0;
+    const uint32_t w = wn;
+    const int bf = f, gn = g + stride;
+    // rotate: points of batch g + 2 stride, cell word of batch g + stride
+    v0 = v1;
+    if (gn + stride < gend) v1 = __ldcs(pts + (size_t)(gn + stride) * 32);
+    if (gn < gend) {
+      if (gn >= fend) {
+        do { ++f; fend += bpf; } while (gn >= fend);
+        fc = load_frame(p, f);
+      }
+      wn = ld_u32(fc.grid + cell_of(v0.x, v0.y, fc));
+    }
+    reinterpret_cast<uint4*>(stage)[lane] = make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(stage)[32 + lane] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    for_each_hit(w, p, bf, prep_of(p, bf, f_smem, prep_smem), v.x, v.y, v.z,
+                 [&](uint32_t t) { stage[lane * W + (t >> 5)] |= 1u << (t & 31u); });
+    __syncwarp();
+    uint4* dst = reinterpret_cast<uint4*>(p.out) + (size_t)g * 64 + lane;
+    __stcs(dst, reinterpret_cast<const uint4*>(stage)[lane]);
+    __stcs(dst + 32, reinterpret_cast<const uint4*>(stage)[32 + lane]);
+    __syncwarp();
+    if (gn >= gend) break;
+    g = gn;
+  }
 }
 
 __global__ void sincos_test_kernel(const float* __restrict__ x, long long n, float* sn, float* cs) {
@@ -858,19 +950,19 @@ __global__ void box_prep_test_kernel(const float* __restrict__ boxes, int T, flo
   }
 }
 
-template <int MODE, int WS, bool VEC4>
+template <int MODE, int WS, bool VEC4, int NT = kStreamThreads, bool GSM = false>
 int launch_stream(const StreamParams& p, int grid, size_t smem, cudaStream_t st) {
   static int configured[64];
   int dev = 0;
   GGA_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && (int)smem > configured[dev] && smem > 48 * 1024) {
     GGA_CHECK_CUDA(
-        cudaFuncSetAttribute(pib_stream_kernel<MODE, WS, VEC4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaFuncSetAttribute(pib_stream_kernel<MODE, WS, VEC4, NT, GSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[dev] = (int)smem;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kStreamThreads);
+  cfg.blockDim = dim3(NT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -878,7 +970,7 @@ int launch_stream(const StreamParams& p, int grid, size_t smem, cudaStream_t st)
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_kernel<MODE, WS, VEC4>, p));
+  GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_kernel<MODE, WS, VEC4, NT, GSM>, p));
   return GGA_OK;
 }
 
@@ -929,7 +1021,7 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   sp.R = (int)R;
   sp.tb_base = (int)(tb / R);
   sp.tb_rem = (int)(tb % R);
-  sp.dynamic = g_tune_dynamic ? 1 : 0;
+  sp.dynamic = 0;
   GGA_REQUIRE(sp.R <= kMaxRanges, "too many ranges");
   sp.vec4 = (pts_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0) ? 1 : 0;
   const int grid = (int)R * occ;
@@ -950,7 +1042,16 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   PrepParams pp;
   pp.boxes = boxes; pp.ws = sp.ws; pp.L = L; pp.T = num_boxes;
   pp.ncache = num_boxes < 2048 ? num_boxes : 2048;
-  const size_t prep_smem = (size_t)3 * (kMaxSliceCells + 4) * 4 + align_up((size_t)num_boxes * 2, 16) +
+  pp.trace = g_trace_prep;
+  {
+    int Gcap = Gmax;  // slices are row bands of the padded grid: ceil((G+2)/S) rows of G+2 cells
+    while (Gcap > 1 && ((Gcap + 2 + S - 1) / S) * (Gcap + 2) > kMaxSliceCells) --Gcap;
+    pp.Gcap = Gcap;
+    pp.max_slice_cells = ((Gcap + 2 + S - 1) / S) * (Gcap + 2);
+    if (pp.max_slice_cells < 9) pp.max_slice_cells = 9;  // G = 1: 3 x 3
+    if (pp.max_slice_cells > kMaxSliceCells) pp.max_slice_cells = kMaxSliceCells;
+  }
+  const size_t prep_smem = (size_t)3 * (kMaxSliceCells + 4) * 4 + align_up((size_t)num_boxes * 12, 16) +
                            (size_t)pp.ncache * kBoxWords * 4;
   {
     static int configured[64];
@@ -962,12 +1063,50 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
       configured[dev] = (int)prep_smem;
     }
   }
-  if (g_tune_phase != 2) {
-    pib_prep_kernel<<<dim3(S, B), kPrepThreads, prep_smem, st>>>(pp);
+  if (g_tune_phase != 2 && g_tune_phase != 3) {
+    pp.S = S;
+  pib_prep_kernel<<<dim3(S + (num_boxes + kPrepThreads - 1) / kPrepThreads, B), kPrepThreads, prep_smem, st>>>(pp);
     GGA_CHECK_CUDA(cudaGetLastError());
   }
   if (g_tune_phase == 1) return GGA_OK;
 
+  if (mode == kModeBits && sp.vec4 && sp.row_words == 8 && sp.smem_prep && (num_points & 31) == 0 && !g_tune_nofast &&
+      kStreamThreads == 256) {
+    const size_t fsmem = (size_t)num_boxes * 32 + (size_t)8 * 32 * 4 * 8;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = fsmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_fast_kernel, sp));
+    return GGA_OK;
+  }
+  {
+    // one 1024-thread CTA per SM with the frame's cell grid in shared memory, when it all fits
+    constexpr int kBig = 1024;
+    const size_t gbytes = L.gstride * 4;
+    const size_t smem_big = gbytes + (sp.smem_prep ? (size_t)num_boxes * 32 : 0) +
+                            (size_t)sp.row_words * 32 * 4 * (kBig / 32);
+    if (mode == kModeBits && sp.vec4 && sp.smem_prep && sp.batch_pts == 32 && smem_big <= 200 * 1024 && g_tune_gsm) {
+      StreamParams bp = sp;
+      bp.grid_smem_words = (int)L.gstride;
+      bp.slots = kBig / 32;
+      long long Rb = (tb + bp.slots - 1) / bp.slots;
+      if (Rb > nsm) Rb = nsm;
+      if (Rb < 1) Rb = 1;
+      bp.R = (int)Rb;
+      bp.tb_base = (int)(tb / Rb);
+      bp.tb_rem = (int)(tb % Rb);
+      if (sp.row_words == 8) return launch_stream<kModeBits, 8, true, kBig, true>(bp, (int)Rb, smem_big, st);
+      return launch_stream<kModeBits, 0, true, kBig, true>(bp, (int)Rb, smem_big, st);
+    }
+  }
+  sp.grid_smem_words = 0;
   if (mode == kModeBits) {
     if (sp.vec4) {
       if (sp.row_words == 8) return launch_stream<kModeBits, 8, true>(sp, grid, smem, st);
@@ -992,7 +1131,10 @@ extern "C" int gga_pib_row_words(int num_boxes) {
 
 extern "C" int gga_pib_set_tuning(int grid_cells, int ctas_per_sm) {
   g_tune_grid = grid_cells;
-  g_tune_dynamic = ctas_per_sm < 0 ? 1 : 0;  // negative: CTA-local dynamic batch draws instead of static strides (experiment hook)
+  g_tune_nogsm = ctas_per_sm < 0 ? 1 : 0;   // negative: never the shared-memory-grid variant of the stream kernel
+  g_tune_nofast = ctas_per_sm != 0 ? 1 : 0;  // any explicit value: never the lean training-shape variant either
+  g_tune_gsm = (ctas_per_sm > 0 && ctas_per_sm >= 100) ? 1 : 0;  // +100: the shared-memory-grid variant (measured: no gain)
+  g_tune_occ %= 100;
   g_tune_occ = ctas_per_sm < 0 ? -ctas_per_sm : ctas_per_sm;
   return GGA_OK;
 }
@@ -1000,6 +1142,10 @@ extern "C" int gga_pib_set_tuning(int grid_cells, int ctas_per_sm) {
 /* profiling hook: device buffer of 16 x uint64 per stream-kernel warp (globaltimer ns, last word = smid) */
 extern "C" int gga_test_pib_trace(void* buf) {
   g_trace = static_cast<unsigned long long*>(buf);
+  return GGA_OK;
+}
+extern "C" int gga_test_pib_trace_prep(void* buf) {
+  g_trace_prep = static_cast<unsigned long long*>(buf);
   return GGA_OK;
 }
 

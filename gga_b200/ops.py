@@ -50,7 +50,7 @@ _WORKSPACES = {}
 def workspace(device, B, M, T):
     """Scratch tensor for one membership call on the CURRENT stream of `device` (the caller of
     the C ABI owns the scratch, include/gga_b200.h).  Cached per (device, stream) and grown on
-    demand; zero-filled once at allocation, as the ABI asks.  Under CUDA-graph capture a
+    demand (its previous contents never matter).  Under CUDA-graph capture a
     private tensor is returned instead (the graph keeps it alive)."""
     L = _lib.load()
     nbytes = int(L.gga_pib_workspace_bytes(int(B), int(M), int(T)))

@@ -51,11 +51,12 @@ int gga_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_m
 int gga_pib_row_words(int num_boxes);
 
 /* Scratch memory of one membership call (the per-frame box index built on the device:
- * contract terms of every box, BEV cell grid, candidate id lists, tile counters).
+ * contract terms of every box, BEV cell grid, candidate id lists).
  * The caller owns it, like every other buffer: device memory, 256-byte aligned, at least
- * gga_pib_workspace_bytes(B, num_points, num_boxes) bytes, zero-filled ONCE after allocation
- * (gga_pib_workspace_init, or any memset); calls leave it ready for the next call.  A
- * workspace must not be shared by calls that can run concurrently (different streams). */
+ * gga_pib_workspace_bytes(B, num_points, num_boxes) bytes; its previous contents do not matter
+ * (every call rebuilds what it reads).  A workspace must not be shared by calls that can run
+ * concurrently (different streams).  gga_pib_workspace_init (a memset) is kept for callers
+ * that want deterministic scratch contents. */
 size_t gga_pib_workspace_bytes(int B, int num_points, int num_boxes);
 int gga_pib_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 
@@ -200,6 +201,8 @@ int gga_test_pib_phase(int phase);
 /* profiling hook: device buffer receiving 16 x uint64 per warp of the streaming kernel
  * (globaltimer stamps; word 15 = SM id); NULL switches tracing off */
 int gga_test_pib_trace(void* device_buffer);
+/* same for the index-build kernel: 16 stamps per CTA, one per phase boundary */
+int gga_test_pib_trace_prep(void* device_buffer);
 int gga_test_sincos(const float* x, int64_t n, float* sn, float* cs, void* stream);
 /* prep : float [num_boxes, 8] = (cx, cy, cz_centre, hz, cosa, sina, hx, hy) */
 int gga_test_box_prep(const float* boxes, int num_boxes, float* prep, void* stream);

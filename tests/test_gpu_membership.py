@@ -214,7 +214,7 @@ def test_tuning_knobs_do_not_change_results():
     ref = om.points_in_boxes_all_np(f['points'], f['boxes'], 8)
     P, B = cu(f['points'])[None], cu(f['boxes'])[None]
     try:
-        for g, c in [(1, 1), (3, 5), (16, 0), (64, 37), (128, 104), (0, -5), (96, -2)]:  # c < 0: CTA-local dynamic batch draws
+        for g, c in [(1, 1), (3, 5), (16, 0), (64, 37), (128, 104), (0, -5), (96, -2)]:  # c < 0: never the shared-memory-grid stream variant
             G.ops.set_tuning(g, c)
             assert np.array_equal(G.unpack_bits(G.points_in_boxes_bits(P, B), 256)[0].cpu().numpy(), ref)
     finally:

@@ -21,8 +21,7 @@ def al(v, a=256): return (v + a - 1) // a * a
 Gmax = int(round(min(64.0 * M, 4.0 * N) ** 0.5)); Gmax = max(4, min(192, Gmax))
 gstride = al((Gmax + 2) ** 2, 4)
 cap = max(8 * Gmax * Gmax, 16 * M + 64); cap = min(cap, (1 << 20) - 2) & ~7
-o_ids_used = 0; off = al(F * 4)
-o_hdr = off; off = al(off + F * 48)
+o_hdr = 0; off = al(F * 48)
 o_prep = off; off = al(off + F * M * 32)
 o_grid = off; off = al(off + F * gstride * 4)
 o_ids = off; off = al(off + F * cap * 2)
@@ -46,4 +45,3 @@ for f in range(min(F, 3)):
     print('  candidates per point: mean %.3f  frac>0 %.3f  max %d ; hist' % (n.mean(), (n > 0).mean(), n.max()), np.bincount(n)[:10])
     mx = n[: N // 32 * 32].reshape(-1, 32).max(1)
     print('  warp-max per 32-batch: mean %.2f  hist' % mx.mean(), np.bincount(mx)[:12])
-print('ids_used after call:', w[:F * 4].view(np.uint32))
