@@ -14,6 +14,6 @@ python bench.py --steps 2000 --warmup 20 > gpurun_out/${TAG}_bench.json 2> gpuru
 cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:pib -s 12 -c 4 -f -o gpurun_out/${TAG}_prof_pib \
+ncu --set full --clock-control none --import-source on -k regex:pib -s 60 -c 4 -f -o gpurun_out/${TAG}_prof_pib \
     python bench.py --steps 12 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out | grep ${TAG}
