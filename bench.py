@@ -335,6 +335,11 @@ def run_ours(args):
     kernel_ms = k0.elapsed_time(k1) / (kreps * n_sets)
     peak, peak_src = peaks()
     achieved = member_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+    try:
+        traffic = int(json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))['membership_dram_bytes_per_launch'])
+    except Exception:
+        pass
 
     # end to end through the public API with HOST buffers (pinned), copies inside the timed region
     hb = host[0]
@@ -374,7 +379,7 @@ def run_ours(args):
             'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_per_step, 5), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
             'roofline': {'bound': 'hbm', 'kernel': 'pib_prep_kernel + pib_stream_fast_kernel (membership, bit-packed; one C call, PDL-chained)', 'achieved': round(achieved, 1),
-                         'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4), 'traffic': None,
+                         'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4), 'traffic': traffic,
                          'peak_source': peak_src, 'kernel_ms': round(kernel_ms, 5),
                          'algorithmic_bytes_per_launch': member_bytes,
                          'step_frac_of_hbm_roofline': round(all_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},

@@ -1,0 +1,158 @@
+// One training-shaped step of the geometry hot path from HOST buffers, entirely behind the C
+// ABI: H2D copies, membership (index build + streaming), projection + loss forward/backward,
+// D2H copies of masks, loss and gradients — what a reference-side caller holding numpy /
+// CPU-tensor data would invoke (the `points_in_boxes_cpu`-style contract of
+// /root/reference/mmdet3d/ops/__init__.py:12,38 extended to the whole step of
+// mmdet3d/models/dense_heads/centerpoint_head_gga.py:629-723).
+//
+// The PCIe link is the bound here (46 MB per step at the training shape), so the step is
+// pipelined frame by frame over a few streams: the H2D copy of frame f+1, the kernels of
+// frame f and the D2H copy of the masks of frame f-1 overlap (full-duplex link); the box
+// kernel and its small copies run on their own stream.  A context owns all device buffers,
+// streams and events, so a call performs no allocation.
+#include <new>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxStreams = 8;
+
+struct StepCtx {
+  int F, N, M, pts_stride, W, device, n_streams;
+  float* d_points;    // [F, N, stride]
+  float* d_boxes;     // [F, M, 7]
+  float* d_proj;      // [F, M, 16]
+  float* d_target;    // [F, M, 4]
+  float* d_weight;    // [F, M]
+  uint32_t* d_bits;   // [F, N, W]
+  float* d_box2d;     // [F*M, 4]
+  float* d_loss;      // [F*M]
+  float* d_loss_sum;  // [1]
+  float* d_grad;      // [F*M, 7]
+  void* d_ws[kMaxStreams];
+  size_t ws_bytes;
+  cudaStream_t streams[kMaxStreams];
+  cudaStream_t box_stream;
+  cudaEvent_t boxes_ready, done[kMaxStreams], box_done;
+};
+
+void destroy(StepCtx* c) {
+  if (!c) return;
+  cudaFree(c->d_points); cudaFree(c->d_boxes); cudaFree(c->d_proj); cudaFree(c->d_target); cudaFree(c->d_weight);
+  cudaFree(c->d_bits); cudaFree(c->d_box2d); cudaFree(c->d_loss); cudaFree(c->d_loss_sum); cudaFree(c->d_grad);
+  for (int i = 0; i < kMaxStreams; ++i) {
+    if (c->d_ws[i]) cudaFree(c->d_ws[i]);
+    if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->done[i]) cudaEventDestroy(c->done[i]);
+  }
+  if (c->box_stream) cudaStreamDestroy(c->box_stream);
+  if (c->boxes_ready) cudaEventDestroy(c->boxes_ready);
+  if (c->box_done) cudaEventDestroy(c->box_done);
+  delete c;
+}
+
+}  // namespace
+
+extern "C" int gga_step_create(int num_frames, int num_points, int num_boxes, int pts_stride, int n_streams,
+                               void** ctx_out) {
+  GGA_REQUIRE(ctx_out != nullptr, "null ctx_out");
+  *ctx_out = nullptr;
+  GGA_REQUIRE(num_frames > 0 && num_points > 0 && num_boxes > 0, "sizes must be positive");
+  GGA_REQUIRE(pts_stride >= 3, "pts_stride must be >= 3 (got %d)", pts_stride);
+  if (n_streams < 1) n_streams = 3;
+  if (n_streams > kMaxStreams) n_streams = kMaxStreams;
+  StepCtx* c = new (std::nothrow) StepCtx();
+  GGA_REQUIRE(c != nullptr, "out of host memory");
+  c->F = num_frames; c->N = num_points; c->M = num_boxes; c->pts_stride = pts_stride;
+  c->W = gga_pib_row_words(num_boxes);
+  c->n_streams = n_streams;
+  const size_t F = num_frames, N = num_points, M = num_boxes;
+  cudaError_t e = cudaGetDevice(&c->device);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_points, F * N * pts_stride * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_boxes, F * M * 7 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_proj, F * M * 16 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_target, F * M * 4 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_weight, F * M * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_bits, F * N * c->W * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_box2d, F * M * 4 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_loss, F * M * 4 * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_loss_sum, sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_grad, F * M * 7 * sizeof(float));
+  c->ws_bytes = gga_pib_workspace_bytes(1, num_points, num_boxes);
+  for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
+    e = cudaMalloc(&c->d_ws[i], c->ws_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->box_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->boxes_ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->box_done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    gga_set_error("gga_step_create: %s", cudaGetErrorString(e));
+    destroy(c);
+    return GGA_ERR_CUDA;
+  }
+  *ctx_out = c;
+  return GGA_OK;
+}
+
+extern "C" int gga_step_destroy(void* ctx) {
+  destroy(static_cast<StepCtx*>(ctx));
+  return GGA_OK;
+}
+
+extern "C" int gga_step_run_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                                 const float* target, const float* weight, int proj_mode, int loss_kind,
+                                 float loss_weight, float avg_factor, float eps, float depth_clamp,
+                                 uint32_t* bits, float* loss_sum, float* grad_boxes) {
+  StepCtx* c = static_cast<StepCtx*>(ctx);
+  GGA_REQUIRE(c != nullptr, "null context");
+  GGA_REQUIRE(points && boxes && lidar2img && target && bits && loss_sum && grad_boxes, "null host pointer");
+  GGA_REQUIRE(avg_factor > 0.f, "avg_factor must be positive");
+  const size_t F = c->F, N = c->N, M = c->M, st = c->pts_stride, W = c->W;
+  int dev = 0;
+  GGA_CHECK_CUDA(cudaGetDevice(&dev));
+  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
+
+  // boxes first: every frame's membership needs them
+  GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_boxes, boxes, F * M * 7 * sizeof(float), cudaMemcpyHostToDevice, c->box_stream));
+  GGA_CHECK_CUDA(cudaEventRecord(c->boxes_ready, c->box_stream));
+  // membership, one frame per pipeline slot
+  for (size_t f = 0; f < F; ++f) {
+    const int s = (int)(f % c->n_streams);
+    cudaStream_t q = c->streams[s];
+    GGA_CHECK_CUDA(cudaStreamWaitEvent(q, c->boxes_ready, 0));
+    GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_points + f * N * st, points + f * N * st, N * st * sizeof(float),
+                                   cudaMemcpyHostToDevice, q));
+    const int rc = gga_points_in_boxes_bits(c->d_points + f * N * st, (int)st, c->d_boxes + f * M * 7,
+                                            c->d_bits + f * N * W, 1, (int)N, (int)M, c->d_ws[s], c->ws_bytes, q);
+    if (rc != GGA_OK) return rc;
+    GGA_CHECK_CUDA(cudaMemcpyAsync(bits + f * N * W, c->d_bits + f * N * W, N * W * sizeof(uint32_t),
+                                   cudaMemcpyDeviceToHost, q));
+  }
+  // projection + loss forward / backward
+  cudaStream_t b = c->box_stream;
+  GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_proj, lidar2img, F * M * 16 * sizeof(float), cudaMemcpyHostToDevice, b));
+  GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_target, target, F * M * 4 * sizeof(float), cudaMemcpyHostToDevice, b));
+  if (weight) GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_weight, weight, F * M * sizeof(float), cudaMemcpyHostToDevice, b));
+  gga_box_loss_args a = {};
+  a.boxes = c->d_boxes; a.proj = c->d_proj; a.proj_stride = 16;
+  a.target = c->d_target;
+  a.weight = weight ? c->d_weight : nullptr; a.weight_cols = 1;
+  a.n = (int)(F * M); a.mode = proj_mode; a.loss_kind = loss_kind;
+  a.depth_clamp = depth_clamp; a.eps = eps; a.grad_scale = loss_weight / avg_factor;
+  a.box2d = c->d_box2d; a.loss = c->d_loss; a.loss_sum = c->d_loss_sum; a.grad_boxes = c->d_grad;
+  const int rc = gga_box_project_loss(&a, b);
+  if (rc != GGA_OK) return rc;
+  GGA_CHECK_CUDA(cudaMemcpyAsync(grad_boxes, c->d_grad, F * M * 7 * sizeof(float), cudaMemcpyDeviceToHost, b));
+  GGA_CHECK_CUDA(cudaMemcpyAsync(loss_sum, c->d_loss_sum, sizeof(float), cudaMemcpyDeviceToHost, b));
+  // the call is synchronous, like the CPU op it stands in for
+  cudaError_t e = cudaStreamSynchronize(b);
+  for (int s = 0; s < c->n_streams && e == cudaSuccess; ++s) e = cudaStreamSynchronize(c->streams[s]);
+  if (e != cudaSuccess) {
+    gga_set_error("gga_step_run_host: %s", cudaGetErrorString(e));
+    return GGA_ERR_CUDA;
+  }
+  return GGA_OK;
+}

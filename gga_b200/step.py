@@ -16,6 +16,8 @@ free and can be captured in a CUDA graph (``capture()`` / ``replay()``).
 ``GeometryStep.run_host`` is the same step for HOST buffers (pinned numpy / torch CPU
 tensors): H2D copies, the kernels, and D2H of masks, loss and gradients.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -118,55 +120,49 @@ class GeometryStep:
         return a
 
     def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3):
-        """Same step with HOST inputs (pinned torch CPU tensors) and HOST results: returns
+        """Same step with HOST inputs (page-locked torch CPU tensors) and HOST results: returns
         (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous.
 
-        The PCIe link is the bound (46 MB per step at the training shape), so the step is
-        pipelined frame by frame over `n_streams` streams: the H2D copy of frame f+1, the
-        membership kernels of frame f and the D2H copy of the masks of frame f-1 overlap
-        (full-duplex link); the box kernel and its small copies run on the calling stream."""
-        dev = self.device
+        One C call (``gga_step_run_host``): the PCIe link is the bound (46 MB per step at the
+        training shape), so the library pipelines the step frame by frame over `n_streams`
+        streams — the H2D copy of frame f+1, the membership kernels of frame f and the D2H copy
+        of the masks of frame f-1 overlap (full-duplex link)."""
         L = self.L
-        if self._host is None:
-            h = {}
-            for name, t in (('points', points), ('boxes', boxes), ('lidar2img', lidar2img),
-                            ('target', target), ('weight', weight)):
-                h['d_' + name] = torch.empty(t.shape, dtype=t.dtype, device=dev)
-            h['h_bits'] = torch.empty(self.bits.shape, dtype=torch.int32).pin_memory()
-            h['h_grad'] = torch.empty(self.grad_boxes.shape, dtype=torch.float32).pin_memory()
-            h['h_loss'] = torch.empty((1,), dtype=torch.float32).pin_memory()
-            h['streams'] = [torch.cuda.Stream(device=dev) for _ in range(max(1, n_streams))]
-            wb = int(L.gga_pib_workspace_bytes(1, self.N, self.M))
-            h['ws'] = [torch.zeros((wb,), dtype=torch.uint8, device=dev) for _ in h['streams']]
-            self._host = h
+        if self._host is None or self._host['n_streams'] != n_streams:
+            self.close()
+            ctx = _lib.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(L.gga_step_create(self.F, self.N, self.M, self.pts_stride, int(n_streams),
+                                             ctypes.byref(ctx)), 'step_create')
+            self._host = dict(
+                ctx=ctx, n_streams=n_streams,
+                h_bits=torch.empty(self.bits.shape, dtype=torch.int32).pin_memory(),
+                h_grad=torch.empty(self.grad_boxes.shape, dtype=torch.float32).pin_memory(),
+                h_loss=torch.empty((1,), dtype=torch.float32).pin_memory())
         h = self._host
-        cur = torch.cuda.current_stream(dev)
-        h['d_boxes'].copy_(boxes, non_blocking=True)
-        boxes_ready = torch.cuda.Event()
-        boxes_ready.record(cur)
-        # membership, one frame per pipeline slot
-        for f in range(self.F):
-            st, ws = h['streams'][f % len(h['streams'])], h['ws'][f % len(h['streams'])]
-            st.wait_event(boxes_ready)
-            with torch.cuda.stream(st):
-                h['d_points'][f].copy_(points[f], non_blocking=True)
-                _lib.check(L.gga_points_in_boxes_bits(h['d_points'][f].data_ptr(), self.pts_stride,
-                                                      h['d_boxes'][f].data_ptr(), self.bits[f].data_ptr(), 1,
-                                                      self.N, self.M, ws.data_ptr(), ws.numel(), st.cuda_stream),
-                           'points_in_boxes_bits')
-                h['h_bits'][f].copy_(self.bits[f], non_blocking=True)
-        # projection + loss forward/backward on the calling stream
-        h['d_lidar2img'].copy_(lidar2img, non_blocking=True)
-        h['d_target'].copy_(target, non_blocking=True)
-        h['d_weight'].copy_(weight, non_blocking=True)
-        a = self._box_args(h['d_boxes'], h['d_lidar2img'], h['d_target'], h['d_weight'], avg_factor)
-        _lib.check(L.gga_box_project_loss(a, cur.cuda_stream), 'box_project_loss')
-        h['h_grad'].copy_(self.grad_boxes, non_blocking=True)
-        h['h_loss'].copy_(self.loss_sum, non_blocking=True)
-        for st in h['streams']:
-            cur.wait_stream(st)
-        cur.synchronize()
+        for t in (points, boxes, lidar2img, target, weight):
+            assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()), \
+                'run_host takes contiguous fp32 CPU tensors'
+        n = self.F * self.M
+        with torch.cuda.device(self.device):
+            _lib.check(L.gga_step_run_host(
+                h['ctx'], points.data_ptr(), boxes.data_ptr(), lidar2img.data_ptr(), target.data_ptr(),
+                None if weight is None else weight.data_ptr(), self.mode, self.kind, self.loss_weight,
+                float(avg_factor if avg_factor is not None else max(n, 1)), self.eps, self.depth_clamp,
+                h['h_bits'].data_ptr(), h['h_loss'].data_ptr(), h['h_grad'].data_ptr()), 'step_run_host')
         return h['h_bits'], float(h['h_loss'][0]), h['h_grad']
+
+    def close(self):
+        """Releases the device context of the host-buffer path (idempotent)."""
+        if self._host is not None:
+            self.L.gga_step_destroy(self._host['ctx'])
+            self._host = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def host_bytes(self, points, boxes, lidar2img, target, weight):
         """(h2d, d2h) bytes moved by one ``run_host``."""

@@ -193,6 +193,27 @@ int gga_image_box_overlap_f64(const double* boxes, int N, const double* query, i
                               int criterion, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * One training-shaped step from HOST buffers (the `points_in_boxes_cpu`-style contract of
+ * /root/reference/mmdet3d/ops/__init__.py:12,38 extended to the whole loss step of
+ * mmdet3d/models/dense_heads/centerpoint_head_gga.py:629-723): H2D copies, membership masks,
+ * projection + loss forward/backward, D2H copies — pipelined frame by frame over `n_streams`
+ * streams (the PCIe link is the bound).  A context owns every device buffer, stream and
+ * event of one (frames, points, boxes) shape on the current device; run calls allocate nothing
+ * and are synchronous.  Host buffers should be page-locked for the copies to overlap.
+ *   points [F, N, pts_stride], boxes [F, M, 7], lidar2img [F, M, 16] (one 4x4 per object),
+ *   target [F, M, 4], weight [F, M] or NULL
+ *   bits uint32 [F, N, gga_pib_row_words(M)], loss_sum [1] (weighted SUM), grad_boxes [F*M, 7]
+ *   (already scaled by loss_weight / avg_factor).
+ * ---------------------------------------------------------------------------------- */
+int gga_step_create(int num_frames, int num_points, int num_boxes, int pts_stride, int n_streams,
+                    void** ctx_out);
+int gga_step_destroy(void* ctx);
+int gga_step_run_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                      const float* target, const float* weight, int proj_mode, int loss_kind,
+                      float loss_weight, float avg_factor, float eps, float depth_clamp,
+                      uint32_t* bits, float* loss_sum, float* grad_boxes);
+
+/* ------------------------------------------------------------------------------------
  * Test hooks (device build of include/gga_detmath.h and of the per-box preparation).
  * ---------------------------------------------------------------------------------- */
 /* profiling hook: 0 = both membership kernels, 1 = index build only, 2 = streaming only
