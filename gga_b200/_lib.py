@@ -56,6 +56,7 @@ SIGNATURES = {
     'gga_match_dt_gt': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p], c_int),
     'gga_image_box_overlap_f64': ([c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
+    'gga_point_box_alignment': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     'gga_step_create': ([c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     'gga_step_destroy': ([c_void_p], c_int),
     'gga_step_run_host': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

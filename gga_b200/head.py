@@ -69,3 +69,82 @@ def boundary_projection_loss(pred_iou, target_box, mask, boundary_mask, code_wei
     loss = box2d_loss(pred_iou, target_box[..., :4], w, avg_factor=(num + 1e-4), kind='l1',
                       reduction='mean', loss_weight=loss_weight)
     return loss * scale
+
+
+# ----------------------------------------------------------------------------------------------
+# Point-to-Box Alignment (PAL): centerpoint_head_gga.py:184-248 (distances), :690-699 (losses)
+# ----------------------------------------------------------------------------------------------
+def pack_in_box_points(ibp_points, device):
+    """``GGA_in_box_points`` — per frame a list (one entry per object) of ``[n_i, >=2]`` tensors
+    (float64 ``(x, y, z, 1)`` in the reference, kitti_converter_gga.py:245-247) — packed ONCE
+    into the CSR layout the kernel reads: (points_xy float32 [P, 2], offsets int32 [n_obj + 1]),
+    objects in frame-major order.  The reference moves every list entry to the device
+    separately (:469-470) and uses only ``[:, :2].float()`` (:201)."""
+    flat = [t for frame in ibp_points for t in frame]
+    counts = torch.tensor([0] + [int(t.shape[0]) for t in flat], dtype=torch.int64)
+    offsets = torch.cumsum(counts, 0).to(torch.int32)
+    if len(flat) and int(offsets[-1]) > 0:
+        xy = torch.cat([t[:, :2].to(torch.float32).cpu() if not t.is_cuda else t[:, :2].to(torch.float32)
+                        for t in flat if t.shape[0] > 0], 0)
+    else:
+        xy = torch.zeros((0, 2), dtype=torch.float32)
+    return xy.to(device).contiguous(), offsets.to(device)
+
+
+class _PointBoxDistances(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, points_xy, offsets, box_bev):
+        from . import _lib
+        assert box_bev.is_cuda and points_xy.is_cuda and offsets.is_cuda, 'CUDA tensors required (no CPU fallback)'
+        n = box_bev.shape[0]
+        bev = box_bev.detach().float().contiguous()
+        xy = points_xy.detach().float().contiguous()
+        off = offsets.to(torch.int32).contiguous()
+        assert off.numel() == n + 1 and bev.shape[1] == 5
+        dist = torch.empty((n, 3), dtype=torch.float32, device=bev.device)
+        jac = torch.empty((n, 3, 5), dtype=torch.float32, device=bev.device)
+        with torch.cuda.device(bev.device):
+            _lib.check(_lib.load().gga_point_box_alignment(_lib.ptr(xy), _lib.ptr(off), _lib.ptr(bev), n,
+                                                           _lib.ptr(dist), _lib.ptr(jac),
+                                                           _lib.current_stream(bev.device)), 'point_box_alignment')
+        ctx.save_for_backward(jac)
+        ctx.in_dtype = box_bev.dtype
+        return dist
+
+    @staticmethod
+    def backward(ctx, g):
+        jac, = ctx.saved_tensors
+        return None, None, torch.einsum('nk,nkj->nj', g.float(), jac).to(ctx.in_dtype)
+
+
+def point_box_distances(points_xy, offsets, box_bev):
+    """Packed form: returns ``dist [n_obj, 3] = (min_dis, x_dis, y_dis)``, differentiable w.r.t.
+    ``box_bev [n_obj, 5] = (cx, cy, w, h, rot)``; one CUDA launch for all objects."""
+    return _PointBoxDistances.apply(points_xy, offsets, box_bev)
+
+
+def get_distance_bev(ibp_points, pred_box_bev, packed=None):
+    """Same signature and return layout as ``CenterHead_GGA.get_distance_bev``
+    (centerpoint_head_gga.py:241-248): ``ibp_points`` = per-frame lists of per-object point
+    tensors, ``pred_box_bev [B, K, 5]``; returns ``(pts_min_dis, pts_x_dis, pts_y_dis)``, each
+    ``[B, K, 1]``.  Pass ``packed=pack_in_box_points(...)`` to skip the per-call packing."""
+    b, k, _ = pred_box_bev.shape
+    xy, off = packed if packed is not None else pack_in_box_points(ibp_points, pred_box_bev.device)
+    assert off.numel() == b * k + 1, f'expected {b * k} objects, got {off.numel() - 1}'
+    d = point_box_distances(xy, off, pred_box_bev.reshape(-1, 5)).reshape(b, k, 3)
+    return d[..., 0:1], d[..., 1:2], d[..., 2:3]
+
+
+def point_alignment_losses(p2c_min, p2c_x, p2c_y, mask, code_weight=0.5, loss_weight=0.25, scale=0.1):
+    """``distancemin / distancex / distancey`` of centerpoint_head_gga.py:690-699: mmdet L1Loss
+    against a zero target, weight ``mask * code_weights[0]``, ``avg_factor = mask.sum() + 1e-4``,
+    ``loss_weight`` 0.25 (gga_kitti_config.py:60), then ``* 0.1``.  Inputs ``[B, K, 1]``, mask ``[B, K]``.
+    The distances are sums of non-negative terms, so L1 against zero is a weighted sum (plain
+    torch ops on [B, K] tensors; the heavy part is the distance kernel)."""
+    num = mask.float().sum()
+    w = (mask.float() * code_weight).unsqueeze(-1)
+    out = []
+    for d in (p2c_min, p2c_x, p2c_y):
+        out.append((d.abs() * w).sum() / (num + 1e-4) * loss_weight * scale)
+    return tuple(out)

@@ -193,6 +193,21 @@ int gga_image_box_overlap_f64(const double* boxes, int N, const double* query, i
                               int criterion, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Point-to-Box Alignment distances (the PAL loss inputs of GGA training) with their Jacobian.
+ * Mirrors CenterHead_GGA.get_distance_single / get_distance_bev,
+ * /root/reference/mmdet3d/models/dense_heads/centerpoint_head_gga.py:184-248 (called :692):
+ * a Python loop over objects with ~20 torch launches each in the reference, one launch here.
+ *   points_xy : float32 [P, 2], the in-box points of all objects, object-major (the
+ *               GGA_in_box_points lists, `clt[..., :2].float()` of :201, packed)
+ *   offsets   : int32 [n_obj + 1] (CSR)
+ *   box_bev   : float32 [n_obj, 5] = (cx, cy, w, h, rot)   (pred_box_bev, :277-286)
+ *   dist      : float32 [n_obj, 3] = (min_dis, x_dis, y_dis)  (p2c_min, p2c_x, p2c_y)
+ *   jac       : optional float32 [n_obj, 3, 5] = d dist / d box_bev
+ * ---------------------------------------------------------------------------------- */
+int gga_point_box_alignment(const float* points_xy, const int32_t* offsets, const float* box_bev,
+                            int n_obj, float* dist, float* jac, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * One training-shaped step from HOST buffers (the `points_in_boxes_cpu`-style contract of
  * /root/reference/mmdet3d/ops/__init__.py:12,38 extended to the whole loss step of
  * mmdet3d/models/dense_heads/centerpoint_head_gga.py:629-723): H2D copies, membership masks,

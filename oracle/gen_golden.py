@@ -233,6 +233,63 @@ def main():
     m['pts'], m['boxes'] = mp, mb
     m['points_in_rbbox'] = ref.box_np_ops.points_in_rbbox(mp, mb)
     np.savez_compressed(os.path.join(OUT, 'ref_rbbox.npz'), **m)
+    # --- GGA head functions, executed from the reference's own source text
+    #     (centerpoint_head_gga.py:167-182 GGA_calculate_rotation, :184-248 get_distance_single/_bev
+    #      = Point-to-Box Alignment distances, :250-341 get_prediction_single), with torch-CPU autograd
+    #     through them; train_cfg of configs/gga/gga_kitti_config.py
+    cfg = dict(grid_size=[1408, 1600, 40], out_size_factor=8, voxel_size=[0.05, 0.05, 0.1],
+               point_cloud_range=[0, -40, -3, 70.4, 40, 1])
+    H = ref_loader.load_head_functions(cfg, norm_bbox=True)
+    hd = {}
+    Bq, Kq = 2, 24
+    fmx = 1408 // 8
+    pred = np.zeros((Bq, Kq, 8), np.float32)
+    pred[..., 0:2] = rng.uniform(0, 1, (Bq, Kq, 2))
+    pred[..., 2] = rng.uniform(-1.5, -0.3, (Bq, Kq))
+    pred[..., 3:6] = np.log(kitti_like_boxes(rng, Bq * Kq)[:, 3:6]).reshape(Bq, Kq, 3)
+    ang = rng.uniform(-np.pi, np.pi, (Bq, Kq))
+    pred[..., 6], pred[..., 7] = np.sin(ang), np.cos(ang)
+    ind = (rng.integers(20, 180, (Bq, Kq)) * fmx + rng.integers(5, 170, (Bq, Kq))).astype(np.int64)
+    l2i = (P2 @ RECT @ TRV2C).astype(np.float32)
+    l2i_all = np.broadcast_to(l2i, (Bq, Kq, 4, 4)).copy()
+    l2i_all[1, ::3, :3, 3] += rng.normal(0, 0.05, (Kq // 3, 3)).astype(np.float32)  # copy-pasted objects keep their own calib
+    tp = torch.from_numpy(pred).clone().requires_grad_(True)
+    rot, rmat = H.GGA_calculate_rotation(tp[..., 6:])
+    ratio, piou, pbev = H.get_prediction_single(tp, torch.from_numpy(ind), torch.from_numpy(l2i_all), rot)
+    gi = torch.from_numpy(rng.normal(size=tuple(piou.shape)).astype(np.float32))
+    gb = torch.from_numpy(rng.normal(size=tuple(pbev.shape)).astype(np.float32))
+    gr = torch.from_numpy(rng.normal(size=tuple(ratio.shape)).astype(np.float32))
+    ((piou * gi).sum() + (pbev * gb).sum() + (ratio * gr).sum()).backward()
+    hd['gps_pred'], hd['gps_ind'], hd['gps_lidar2img'] = pred, ind, l2i_all
+    hd['gps_rot'], hd['gps_ratio'], hd['gps_iou'], hd['gps_bev'] = (rot.detach().numpy(), ratio.detach().numpy(),
+                                                                     piou.detach().numpy(), pbev.detach().numpy())
+    hd['gps_gi'], hd['gps_gb'], hd['gps_gr'], hd['gps_grad_pred'] = gi.numpy(), gb.numpy(), gr.numpy(), tp.grad.numpy()
+    # Point-to-Box Alignment: ragged in-box point lists (float64 [n_i, 4] = x, y, z, 1 like
+    # kitti_converter_gga.py:245-247), some empty, some far outside the predicted box
+    bev = pbev.detach().clone().requires_grad_(True)
+    lists, counts = [], []
+    for b_ in range(Bq):
+        row = []
+        for k_ in range(Kq):
+            n_i = int(rng.choice([0, 1, 3, 17, 64, 300, 1500]))
+            cx, cy, w_, h_, r_ = bev[b_, k_].detach().numpy()
+            loc = rng.uniform(-0.9, 0.9, (n_i, 2)) * np.array([w_, h_]) * rng.choice([0.5, 1.0, 3.0])
+            c_, s_ = np.cos(r_), np.sin(r_)
+            xy = np.stack([cx + loc[:, 0] * c_ - loc[:, 1] * s_, cy + loc[:, 0] * s_ + loc[:, 1] * c_], 1)
+            pts4 = np.concatenate([xy, rng.uniform(-2, 0, (n_i, 1)), np.ones((n_i, 1))], 1).astype(np.float64)
+            row.append(torch.from_numpy(pts4))
+            counts.append(n_i)
+        lists.append(row)
+    dmin, dxs, dys = H.get_distance_bev(lists, bev)
+    cm, cx_, cy_ = (torch.from_numpy(rng.uniform(0.5, 1.5, tuple(dmin.shape)).astype(np.float32)) for _ in range(3))
+    ((dmin * cm).sum() + (dxs * cx_).sum() + (dys * cy_).sum()).backward()
+    hd['pal_bev'] = bev.detach().numpy()
+    hd['pal_counts'] = np.asarray(counts, np.int32)
+    hd['pal_points_xy'] = np.concatenate([t[:, :2].numpy() for row in lists for t in row], 0)   # float64, object-major
+    hd['pal_min'], hd['pal_x'], hd['pal_y'] = dmin.detach().numpy(), dxs.detach().numpy(), dys.detach().numpy()
+    hd['pal_cm'], hd['pal_cx'], hd['pal_cy'] = cm.numpy(), cx_.numpy(), cy_.numpy()
+    hd['pal_grad_bev'] = bev.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, 'ref_head.npz'), **hd)
     print('wrote', sorted(os.listdir(OUT)))
 
 

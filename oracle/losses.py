@@ -192,3 +192,54 @@ def match_dt_to_gt(dt_boxes, gt_boxes):
         return np.full((ov.shape[0],), -1, np.int64), np.zeros((ov.shape[0],))
     m = np.argmax(ov, axis=-1)
     return m, ov[np.arange(ov.shape[0]), m]
+
+
+def point_box_distances(points_xy, offsets, box_bev):
+    """Point-to-Box Alignment distances: ``CenterHead_GGA.get_distance_single`` /
+    ``get_distance_bev`` (centerpoint_head_gga.py:184-248), restated on a CSR layout.
+
+    points_xy [P, 2] float32 (the ``clt[..., :2].float()`` of :201), object-major;
+    offsets int [n_obj + 1]; box_bev [n_obj, 5] = (cx, cy, w, h, rot) (:277-286).
+    Returns (min_dis, x_dis, y_dis), each [n_obj] (the reference's ``[B, K, 1]`` flattened):
+      rotate points and centre clockwise by rot (utils.py:28-117, 2-D branch, clockwise):
+        x' = x cos + y sin,  y' = -x sin + y cos
+      min_dis = sum_p min(|x' - (cx' -+ w/2)|, |y' - (cy' -+ h/2)|)          (:209-227)
+      x_dis   = sum_p relu(|x' - cx'| - 2 (w/2)),  y_dis likewise with h     (:215-219,228-229)
+    Differentiable w.r.t. box_bev (torch autograd is the gradient oracle).
+    """
+    n = box_bev.shape[0]
+    mins, xs, ys = [], [], []
+    for i in range(n):
+        clt = points_xy[int(offsets[i]):int(offsets[i + 1])]
+        cx, cy, w, h, rot = box_bev[i, 0], box_bev[i, 1], box_bev[i, 2], box_bev[i, 3], box_bev[i, 4]
+        c, s = torch.cos(rot), torch.sin(rot)
+        px = clt[:, 0] * c + clt[:, 1] * s
+        py = clt[:, 0] * (-s) + clt[:, 1] * c
+        cxr = cx * c + cy * s
+        cyr = cx * (-s) + cy * c
+        half_l, half_h = w / 2.0, h / 2.0
+        dx1, dx2 = px - (cxr - half_l), px - (cxr + half_l)
+        dy1, dy2 = py - (cyr - half_h), py - (cyr + half_h)
+        dx = torch.relu(torch.abs(px - cxr) - 2 * half_l)
+        dy = torch.relu(torch.abs(py - cyr) - 2 * half_h)
+        dis = torch.abs(torch.stack([dx1, dx2, dy1, dy2]).transpose(1, 0))
+        all_dis = torch.min(dis, dim=-1)[0] if clt.shape[0] else dis.new_zeros((0,))
+        mins.append(all_dis.sum())
+        xs.append(dx.sum())
+        ys.append(dy.sum())
+    if n == 0:
+        z = box_bev.new_zeros((0,))
+        return z, z, z
+    return torch.stack(mins), torch.stack(xs), torch.stack(ys)
+
+
+def point_alignment_losses(min_dis, x_dis, y_dis, mask, code_weight=0.5, loss_weight=0.25, scale=0.1):
+    """The three PAL terms of centerpoint_head_gga.py:690-699: mmdet ``L1Loss`` against a zero
+    target, weight = mask * code_weights[0], avg_factor = mask.sum() + 1e-4, then * 0.1.
+    min_dis / x_dis / y_dis / mask: [B, K]."""
+    num = mask.float().sum()
+    w = mask.float() * code_weight
+    out = []
+    for d in (min_dis, x_dis, y_dis):
+        out.append(l1_loss_module(d, torch.zeros_like(d), w, avg_factor=(num + 1e-4), loss_weight=loss_weight) * scale)
+    return tuple(out)

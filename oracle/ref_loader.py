@@ -142,3 +142,38 @@ def load_reference(points_in_boxes_all=None, points_in_boxes_part=None):
         mmcv_ops=ops)
     _CACHE['ns'] = ns
     return ns
+
+
+def load_head_functions(train_cfg, norm_bbox=True):
+    """The GGA head methods of the reference, extracted from its source file and bound to a
+    stand-in ``self`` (the module itself cannot be imported: its header needs mmcv.cnn and the
+    mmdet registries, ``centerpoint_head_gga.py:5-15``).  Returns a namespace with the
+    reference's OWN ``GGA_calculate_rotation`` (:167-182), ``get_distance_single`` (:184-239),
+    ``get_distance_bev`` (:241-248) and ``get_prediction_single`` (:250-341), executing the
+    reference source text unmodified."""
+    import ast
+    import numpy as np
+    import torch
+    ns = load_reference()
+    path = os.path.join(REF_ROOT, 'mmdet3d/models/dense_heads/centerpoint_head_gga.py')
+    tree = ast.parse(open(path).read(), filename=path)
+    wanted = {'GGA_calculate_rotation', 'get_distance_single', 'get_distance_bev', 'get_prediction_single'}
+    funcs = [n for cls in tree.body if isinstance(cls, ast.ClassDef) and cls.name == 'CenterHead_GGA'
+             for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {f.name for f in funcs} == wanted, [f.name for f in funcs]
+
+    def multi_apply(func, *args, **kwargs):   # mmdet.core.multi_apply [un-vendored], restated
+        from functools import partial
+        pfunc = partial(func, **kwargs) if kwargs else func
+        return tuple(map(list, zip(*map(pfunc, *args))))
+
+    glb = {'torch': torch, 'np': np, 'multi_apply': multi_apply, 'rotation_3d_in_axis': ns.rotation_3d_in_axis,
+           '__builtins__': __builtins__}
+    mod = ast.Module(body=funcs, type_ignores=[])
+    exec(compile(mod, path, 'exec'), glb)
+    self = types.SimpleNamespace(train_cfg=train_cfg, norm_bbox=norm_bbox)
+    out = types.SimpleNamespace()
+    for name in wanted:
+        setattr(self, name, types.MethodType(glb[name], self))
+        setattr(out, name, getattr(self, name))
+    return out
