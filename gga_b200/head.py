@@ -77,8 +77,8 @@ def boundary_projection_loss(pred_iou, target_box, mask, boundary_mask, code_wei
 def pack_in_box_points(ibp_points, device):
     """``GGA_in_box_points`` — per frame a list (one entry per object) of ``[n_i, >=2]`` tensors
     (float64 ``(x, y, z, 1)`` in the reference, kitti_converter_gga.py:245-247) — packed ONCE
-    into the CSR layout the kernel reads: (points_xy float32 [P, 2], offsets int32 [n_obj + 1]),
-    objects in frame-major order.  The reference moves every list entry to the device
+    into the CSR layout the kernel reads: (points_xy float32 [P, 2], offsets int32 [n_obj + 1],
+    max_points int), objects in frame-major order.  The reference moves every list entry to the device
     separately (:469-470) and uses only ``[:, :2].float()`` (:201)."""
     flat = [t for frame in ibp_points for t in frame]
     counts = torch.tensor([0] + [int(t.shape[0]) for t in flat], dtype=torch.int64)
@@ -88,13 +88,13 @@ def pack_in_box_points(ibp_points, device):
                         for t in flat if t.shape[0] > 0], 0)
     else:
         xy = torch.zeros((0, 2), dtype=torch.float32)
-    return xy.to(device).contiguous(), offsets.to(device)
+    return xy.to(device).contiguous(), offsets.to(device), int(counts.max())
 
 
 class _PointBoxDistances(torch.autograd.Function):
 
     @staticmethod
-    def forward(ctx, points_xy, offsets, box_bev):
+    def forward(ctx, points_xy, offsets, box_bev, max_points):
         from . import _lib
         assert box_bev.is_cuda and points_xy.is_cuda and offsets.is_cuda, 'CUDA tensors required (no CPU fallback)'
         n = box_bev.shape[0]
@@ -104,10 +104,12 @@ class _PointBoxDistances(torch.autograd.Function):
         assert off.numel() == n + 1 and bev.shape[1] == 5
         dist = torch.empty((n, 3), dtype=torch.float32, device=bev.device)
         jac = torch.empty((n, 3, 5), dtype=torch.float32, device=bev.device)
+        L = _lib.load()
+        ws = torch.empty((int(L.gga_pal_workspace_bytes(n, int(max_points))),), dtype=torch.uint8, device=bev.device)
         with torch.cuda.device(bev.device):
-            _lib.check(_lib.load().gga_point_box_alignment(_lib.ptr(xy), _lib.ptr(off), _lib.ptr(bev), n,
-                                                           _lib.ptr(dist), _lib.ptr(jac),
-                                                           _lib.current_stream(bev.device)), 'point_box_alignment')
+            _lib.check(L.gga_point_box_alignment(_lib.ptr(xy), _lib.ptr(off), _lib.ptr(bev), n, int(max_points),
+                                                 _lib.ptr(dist), _lib.ptr(jac), _lib.ptr(ws), ws.numel(),
+                                                 _lib.current_stream(bev.device)), 'point_box_alignment')
         ctx.save_for_backward(jac)
         ctx.in_dtype = box_bev.dtype
         return dist
@@ -115,13 +117,18 @@ class _PointBoxDistances(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         jac, = ctx.saved_tensors
-        return None, None, torch.einsum('nk,nkj->nj', g.float(), jac).to(ctx.in_dtype)
+        return None, None, torch.einsum('nk,nkj->nj', g.float(), jac).to(ctx.in_dtype), None
 
 
-def point_box_distances(points_xy, offsets, box_bev):
+def point_box_distances(points_xy, offsets, box_bev, max_points=None):
     """Packed form: returns ``dist [n_obj, 3] = (min_dis, x_dis, y_dis)``, differentiable w.r.t.
-    ``box_bev [n_obj, 5] = (cx, cy, w, h, rot)``; one CUDA launch for all objects."""
-    return _PointBoxDistances.apply(points_xy, offsets, box_bev)
+    ``box_bev [n_obj, 5] = (cx, cy, w, h, rot)``; two CUDA launches for all objects.
+    ``max_points`` = upper bound of the per-object list length (from ``pack_in_box_points``;
+    computed here with a device sync when omitted)."""
+    if max_points is None:
+        o = offsets.to(torch.int64)
+        max_points = int((o[1:] - o[:-1]).max().item()) if o.numel() > 1 else 0
+    return _PointBoxDistances.apply(points_xy, offsets, box_bev, int(max_points))
 
 
 def get_distance_bev(ibp_points, pred_box_bev, packed=None):
@@ -130,9 +137,9 @@ def get_distance_bev(ibp_points, pred_box_bev, packed=None):
     tensors, ``pred_box_bev [B, K, 5]``; returns ``(pts_min_dis, pts_x_dis, pts_y_dis)``, each
     ``[B, K, 1]``.  Pass ``packed=pack_in_box_points(...)`` to skip the per-call packing."""
     b, k, _ = pred_box_bev.shape
-    xy, off = packed if packed is not None else pack_in_box_points(ibp_points, pred_box_bev.device)
+    xy, off, mx = packed if packed is not None else pack_in_box_points(ibp_points, pred_box_bev.device)
     assert off.numel() == b * k + 1, f'expected {b * k} objects, got {off.numel() - 1}'
-    d = point_box_distances(xy, off, pred_box_bev.reshape(-1, 5)).reshape(b, k, 3)
+    d = point_box_distances(xy, off, pred_box_bev.reshape(-1, 5), mx).reshape(b, k, 3)
     return d[..., 0:1], d[..., 1:2], d[..., 2:3]
 
 

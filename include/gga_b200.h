@@ -203,9 +203,17 @@ int gga_image_box_overlap_f64(const double* boxes, int N, const double* query, i
  *   box_bev   : float32 [n_obj, 5] = (cx, cy, w, h, rot)   (pred_box_bev, :277-286)
  *   dist      : float32 [n_obj, 3] = (min_dis, x_dis, y_dis)  (p2c_min, p2c_x, p2c_y)
  *   jac       : optional float32 [n_obj, 3, 5] = d dist / d box_bev
+ *   max_points_per_object : upper bound of the list lengths (a host-side number known when the
+ *               lists are packed; the reference caps them at 6000, kitti_converter_gga.py:410-413).
+ *               Objects are split into 512-point chunks served by one warp each; an object with
+ *               more points than the bound is an error of the caller (points beyond are ignored).
+ *   workspace : caller-owned scratch for the per-chunk partial sums, gga_pal_workspace_bytes()
+ *               bytes, any contents; results are summed in chunk order (deterministic).
  * ---------------------------------------------------------------------------------- */
+size_t gga_pal_workspace_bytes(int n_obj, int max_points_per_object);
 int gga_point_box_alignment(const float* points_xy, const int32_t* offsets, const float* box_bev,
-                            int n_obj, float* dist, float* jac, void* stream);
+                            int n_obj, int max_points_per_object, float* dist, float* jac,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * One training-shaped step from HOST buffers (the `points_in_boxes_cpu`-style contract of

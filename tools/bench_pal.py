@@ -33,10 +33,13 @@ def main():
     L = G._lib.load()
     dist = torch.empty((n_obj, 3), device='cuda')
     jac = torch.empty((n_obj, 3, 5), device='cuda')
+    mx = int(counts.max())
+    ws = torch.empty((int(L.gga_pal_workspace_bytes(n_obj, mx)),), dtype=torch.uint8, device='cuda')
 
     def call():
-        assert L.gga_point_box_alignment(dxy.data_ptr(), doff.data_ptr(), dbev.data_ptr(), n_obj, dist.data_ptr(),
-                                         jac.data_ptr(), torch.cuda.current_stream().cuda_stream) == 0
+        assert L.gga_point_box_alignment(dxy.data_ptr(), doff.data_ptr(), dbev.data_ptr(), n_obj, mx, dist.data_ptr(),
+                                         jac.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         torch.cuda.current_stream().cuda_stream) == 0
     for _ in range(3):
         call()
     torch.cuda.synchronize()
