@@ -53,6 +53,8 @@ SIGNATURES = {
                                   c_void_p, c_int, c_int, ctypes.c_float, c_void_p], c_int),
     'gga_box2d_loss': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, ctypes.c_float,
                         ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+    'gga_box3d_aa_loss': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float, ctypes.c_float,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
     'gga_match_dt_gt': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p], c_int),
     'gga_image_box_overlap_f64': ([c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),

@@ -35,7 +35,8 @@ def install(patch_mmcv=True, register_losses=True):
                 reg = __import__(regmod, fromlist=['LOSSES']).LOSSES
             except Exception:
                 continue
-            for cls in (losses.ProjectedGIoULoss, losses.ProjectedIoULoss, losses.ProjectedL1Loss):
+            for cls in (losses.ProjectedGIoULoss, losses.ProjectedIoULoss, losses.ProjectedL1Loss,
+                        losses.AxisAlignedIoULoss):
                 try:
                     reg.register_module(module=cls, force=True)
                     done.append(f'{regmod}.LOSSES.{cls.__name__}')

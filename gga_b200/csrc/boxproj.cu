@@ -502,6 +502,106 @@ __global__ void __launch_bounds__(kBoxThreads) box2d_loss_kernel(
   }
 }
 
+// Axis-aligned 3-D IoU / GIoU loss of aligned box pairs (x1, y1, z1, x2, y2, z2): the vendored
+// formula of /root/reference/mmdet3d/core/bbox/iou_calculators/iou3d_calculator.py:281-329
+// (is_aligned) under AxisAlignedIoULoss (mmdet3d/models/losses/axis_aligned_iou_loss.py:10-82):
+// loss = 1 - iou (or 1 - giou).  Same tie / clamp gradient conventions as the 2-D family.
+__device__ __forceinline__ float aa3d_loss(const float p[6], const float t[6], bool giou, float eps,
+                                           float gp[6], float gt[6]) {
+  float pe[3], te[3], dw[3], w[3], lt[3], rb[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    pe[k] = p[3 + k] - p[k];
+    te[k] = t[3 + k] - t[k];
+    lt[k] = fmaxf(p[k], t[k]);
+    rb[k] = fminf(p[3 + k], t[3 + k]);
+    dw[k] = rb[k] - lt[k];
+    w[k] = fmaxf(dw[k], 0.f);
+  }
+  const float area1 = pe[0] * pe[1] * pe[2], area2 = te[0] * te[1] * te[2];
+  const float overlap = w[0] * w[1] * w[2];
+  const float uni = area1 + area2 - overlap;
+  const float uc = fmaxf(uni, eps);
+  const float iou = overlap / uc;
+  float loss = 1.f - iou, g_uc = overlap / (uc * uc), g_ea = 0.f;  // d loss / d uc ; g_iou = -1
+  float edw[3] = {0.f, 0.f, 0.f}, ew[3] = {0.f, 0.f, 0.f}, ea = 0.f, eac = 1.f;
+  if (giou) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      edw[k] = fmaxf(p[3 + k], t[3 + k]) - fminf(p[k], t[k]);
+      ew[k] = fmaxf(edw[k], 0.f);
+    }
+    ea = ew[0] * ew[1] * ew[2];
+    eac = fmaxf(ea, eps);
+    loss = 1.f - (iou - (eac - uc) / eac);
+    g_uc += -1.f / eac;
+    g_ea = uc / (eac * eac);
+  }
+  const float g_uni = g_uc * tie_hi(uni, eps);
+  const float g_ov = -1.f / uc - g_uni;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+    const float g_w = g_ov * w[k1] * w[k2] * (dw[k] >= 0.f ? 1.f : 0.f);
+    gp[k] = -g_w * tie_hi(p[k], t[k]) - g_uni * pe[k1] * pe[k2];
+    gt[k] = -g_w * tie_hi(t[k], p[k]) - g_uni * te[k1] * te[k2];
+    gp[3 + k] = g_w * tie_lo(p[3 + k], t[3 + k]) + g_uni * pe[k1] * pe[k2];
+    gt[3 + k] = g_w * tie_lo(t[3 + k], p[3 + k]) + g_uni * te[k1] * te[k2];
+    if (giou) {
+      const float g_ew = g_ea * tie_hi(ea, eps) * ew[k1] * ew[k2] * (edw[k] >= 0.f ? 1.f : 0.f);
+      gp[k] += -g_ew * tie_lo(p[k], t[k]);
+      gt[k] += -g_ew * tie_lo(t[k], p[k]);
+      gp[3 + k] += g_ew * tie_hi(p[3 + k], t[3 + k]);
+      gt[3 + k] += g_ew * tie_hi(t[3 + k], p[3 + k]);
+    }
+  }
+  return loss;
+}
+
+__global__ void __launch_bounds__(kBoxThreads) box3d_aa_loss_kernel(
+    const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ weight,
+    const float* __restrict__ grad_loss, int n, int giou, float eps, float grad_scale, float* loss,
+    float* loss_sum, float* grad_pred, float* grad_target, float* partial, unsigned int* counter) {
+  __shared__ float warp_sum[kBoxThreads / 32];
+  __shared__ bool is_last;
+  float my_sum = 0.f;
+  for (int i = blockIdx.x * kBoxThreads + threadIdx.x; i < n; i += gridDim.x * kBoxThreads) {
+    float p[6], t[6], gp[6], gt[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { p[k] = __ldg(pred + (size_t)i * 6 + k); t[k] = __ldg(target + (size_t)i * 6 + k); }
+    const float l = aa3d_loss(p, t, giou != 0, eps, gp, gt);
+    const float wi = weight ? __ldg(weight + i) : 1.f;
+    const float up = (grad_loss ? __ldg(grad_loss + i) : grad_scale) * wi;
+    if (loss) loss[i] = l;
+    my_sum += l * wi;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (grad_pred) grad_pred[(size_t)i * 6 + k] = gp[k] * up;
+      if (grad_target) grad_target[(size_t)i * 6 + k] = gt[k] * up;
+    }
+  }
+  if (!loss_sum) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_sum += __shfl_xor_sync(0xffffffffu, my_sum, o);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = my_sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kBoxThreads / 32; ++w) s += warp_sum[w];
+    partial[blockIdx.x] = s;
+    __threadfence();
+    is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (unsigned int k = 0; k < gridDim.x; ++k) s += __ldcg(partial + k);
+    *loss_sum = s;
+    *counter = 0u;
+  }
+}
+
 int blocks_for(int n) {
   int blocks = (n + kBoxThreads - 1) / kBoxThreads;
   if (blocks > kMaxPartials) blocks = kMaxPartials;
@@ -593,6 +693,35 @@ extern "C" int gga_box2d_loss(const float* pred, const float* target, const floa
                                                            n, loss_kind, eps, grad_scale, loss,
                                                            loss_sum, grad_pred, grad_target, partial,
                                                            counter);
+  GGA_CHECK_CUDA(cudaGetLastError());
+  return GGA_OK;
+}
+
+extern "C" int gga_box3d_aa_loss(const float* pred, const float* target, const float* weight,
+                                 const float* grad_loss, int n, int giou, float eps, float grad_scale,
+                                 float* loss, float* loss_sum, float* grad_pred, float* grad_target,
+                                 void* stream) {
+  GGA_REQUIRE(n >= 0, "negative n");
+  cudaStream_t st = gga_stream(stream);
+  if (n == 0) {
+    if (loss_sum) GGA_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(float), st));
+    return GGA_OK;
+  }
+  GGA_REQUIRE(pred && target, "null pred/target");
+  GGA_REQUIRE(eps > 0.f, "eps must be positive");
+  float* partial = nullptr;
+  unsigned int* counter = nullptr;
+  if (loss_sum) {
+    Workspace* ws;
+    const int rc = get_workspace(&ws);
+    if (rc != GGA_OK) return rc;
+    const unsigned int slot = (g_slot++) % kSlots;
+    partial = ws->partial[slot];
+    counter = &ws->counter[slot];
+  }
+  box3d_aa_loss_kernel<<<blocks_for(n), kBoxThreads, 0, st>>>(pred, target, weight, grad_loss, n, giou, eps,
+                                                              grad_scale, loss, loss_sum, grad_pred,
+                                                              grad_target, partial, counter);
   GGA_CHECK_CUDA(cudaGetLastError());
   return GGA_OK;
 }

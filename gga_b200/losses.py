@@ -225,3 +225,74 @@ def projected_box_loss(boxes, proj, target, weight=None, avg_factor=None, kind='
     n_elems = boxes.numel() // 7 * (4 if k == _lib.LOSS_L1 else 1)
     out = s * _reduce(s, n_elems, reduction, avg_factor, loss_weight)
     return (out, box2d, valid) if return_box2d else out
+
+
+# ----------------------------------------------------------------------------------------------
+# AxisAlignedIoULoss (3-D, FCAF3D): mmdet3d/models/losses/axis_aligned_iou_loss.py:10-82
+# ----------------------------------------------------------------------------------------------
+class _Box3DAALoss(torch.autograd.Function):
+    """Σ_i w_i (1 - iou_i) (or the per-pair vector) over aligned [.., 6] boxes + gradients."""
+
+    @staticmethod
+    def forward(ctx, pred, target, weight, giou, eps, per_box):
+        dev = pred.device
+        lead = pred.shape[:-1]
+        p = pred.detach().reshape(-1, 6).float().contiguous()
+        t = target.detach().reshape(-1, 6).float().contiguous()
+        n = p.shape[0]
+        w = None if weight is None else weight.detach().to(device=dev, dtype=torch.float32).reshape(n).contiguous()
+        loss = torch.empty((n,), dtype=torch.float32, device=dev)
+        loss_sum = torch.empty((1,), dtype=torch.float32, device=dev)
+        gp = torch.empty((n, 6), dtype=torch.float32, device=dev)
+        gt = torch.empty((n, 6), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().gga_box3d_aa_loss(_lib.ptr(p), _lib.ptr(t), _lib.ptr(w), None, n, int(giou),
+                                                     float(eps), 1.0, _lib.ptr(loss), _lib.ptr(loss_sum),
+                                                     _lib.ptr(gp), _lib.ptr(gt), _lib.current_stream(dev)),
+                       'box3d_aa_loss')
+        ctx.save_for_backward(gp, gt)
+        ctx.per_box, ctx.shape = per_box, pred.shape
+        if per_box:
+            return (loss * w if w is not None else loss).reshape(lead)
+        return loss_sum.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        gp, gt = ctx.saved_tensors
+        if ctx.per_box:
+            g = g.reshape(-1, 1).float()
+        return (gp * g).reshape(ctx.shape), (gt * g).reshape(ctx.shape), None, None, None, None
+
+
+def axis_aligned_iou_loss(pred, target, weight=None, avg_factor=None, reduction='mean', loss_weight=1.0,
+                          mode='iou', eps=1e-6):
+    """Functional form of ``AxisAlignedIoULoss`` on [..., 6] CUDA boxes (x1, y1, z1, x2, y2, z2)."""
+    assert pred.is_cuda, 'axis_aligned_iou_loss needs CUDA tensors (no CPU fallback)'
+    assert mode in ('iou', 'giou')
+    n = pred.numel() // 6
+    if reduction == 'none':
+        return loss_weight * _Box3DAALoss.apply(pred, target, weight, mode == 'giou', eps, True)
+    s = _Box3DAALoss.apply(pred, target, weight, mode == 'giou', eps, False)
+    return s * _reduce(s, n, reduction, avg_factor, loss_weight)
+
+
+class AxisAlignedIoULoss(nn.Module):
+    """Same constructor / forward signature as the reference module
+    (``axis_aligned_iou_loss.py:30-82``): ``loss = 1 - iou`` of aligned axis-aligned 3-D boxes,
+    mmdet ``weighted_loss`` reduction, early-out ``(pred * weight).sum()`` when no weight is
+    positive (:74-76)."""
+
+    def __init__(self, reduction='mean', loss_weight=1.0):
+        super().__init__()
+        assert reduction in ['none', 'sum', 'mean']
+        self.reduction = reduction
+        self.loss_weight = loss_weight
+
+    def forward(self, pred, target, weight=None, avg_factor=None, reduction_override=None, **kwargs):
+        assert reduction_override in (None, 'none', 'mean', 'sum')
+        reduction = reduction_override if reduction_override else self.reduction
+        if (weight is not None) and (not torch.any(weight > 0)) and (reduction != 'none'):
+            if weight.dim() == pred.dim() - 1:
+                weight = weight.unsqueeze(-1)
+            return (pred * weight).sum()
+        return axis_aligned_iou_loss(pred, target, weight, avg_factor, reduction, self.loss_weight)

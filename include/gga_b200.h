@@ -171,6 +171,15 @@ int gga_box2d_loss(const float* pred, const float* target, const float* weight, 
                    const float* grad_loss, int n, int loss_kind, float eps, float grad_scale,
                    float* loss, float* loss_sum, float* grad_pred, float* grad_target, void* stream);
 
+/* Axis-aligned 3-D IoU (giou = 0) / GIoU (giou = 1) loss of aligned pairs, boxes [n, 6] =
+ * (x1, y1, z1, x2, y2, z2): AxisAlignedIoULoss, /root/reference/mmdet3d/models/losses/
+ * axis_aligned_iou_loss.py:10-82, over axis_aligned_bbox_overlaps_3d (is_aligned),
+ * mmdet3d/core/bbox/iou_calculators/iou3d_calculator.py:281-329 — the FCAF3D box loss
+ * (fcaf3d_head.py:59,313-318).  loss = 1 - iou; weight [n] or NULL; outputs as gga_box2d_loss. */
+int gga_box3d_aa_loss(const float* pred, const float* target, const float* weight,
+                      const float* grad_loss, int n, int giou, float eps, float grad_scale,
+                      float* loss, float* loss_sum, float* grad_pred, float* grad_target, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Matching — block-diagonal pairwise 2D IoU + argmax (pseudo-label matching).
  * Mirrors image_box_overlap (/root/reference/mmdet3d/core/evaluation/kitti_utils/eval.py:85-114,

@@ -292,3 +292,38 @@ def test_convert_valid_bboxes_batch_matches_oracle():
                                              synth.KITTI_MATCH_RANGE)
         assert close(out['bbox'][torch.as_tensor(sel).cuda()], b2d)
         assert np.array_equal(out['valid'].cpu().numpy()[sel], valid.numpy())
+
+
+def test_axis_aligned_iou_loss_3d_vs_reference_golden_and_oracle(golden_dir):
+    """AxisAlignedIoULoss (FCAF3D): known answer of the reference's test_losses.py:178-189,
+    golden IoU / GIoU of axis_aligned_bbox_overlaps_3d, and oracle gradients."""
+    import os
+    d = np.load(os.path.join(golden_dir, 'ref_iou.npz'))
+    q1, q2 = torch.from_numpy(d['q1']).cuda(), torch.from_numpy(d['q2']).cuda()
+    for mode, key in (('iou', 'aa3d_iou_3d'), ('giou', 'aa3d_giou_3d')):
+        l = G.axis_aligned_iou_loss(q1, q2, reduction='none', mode=mode)
+        assert np.allclose(1.0 - l.cpu().numpy(), d[key], rtol=1e-5, atol=1e-6)
+    # the reference's own unit test vector
+    loss = G.AxisAlignedIoULoss(reduction='mean')
+    pred = torch.tensor([[0., 0, 0, 1, 1, 1], [0, 0, 0, 1, 1, 1], [0, 0, 0, 1, 1, 1]]).cuda()
+    tgt = torch.tensor([[0., 0, 0, 1, 1, 1], [-4, -4, -4, -1, -1, -1], [0, 0, 0, 0.5, 0.5, 0.5]]).cuda()   # disjoint / contained
+    out = loss(pred, tgt, reduction_override='none')
+    assert np.allclose(out.cpu().numpy(), [0.0, 1.0, 1.0 - 0.125], atol=1e-6)
+    # gradients and weighted reduction against the oracle (torch autograd on the restated formula)
+    rng = np.random.default_rng(9)
+    lo = rng.uniform(-2, 2, (500, 3)); a = np.concatenate([lo, lo + rng.uniform(0.1, 3, (500, 3))], 1).astype(np.float32)
+    lo2 = lo + rng.normal(0, 0.7, (500, 3)); b = np.concatenate([lo2, lo2 + rng.uniform(0.1, 3, (500, 3))], 1).astype(np.float32)
+    a[:5] = b[:5]                                     # exact ties
+    w = rng.uniform(0, 2, 500).astype(np.float32)
+    pa = torch.from_numpy(a).requires_grad_(True); pb = torch.from_numpy(b).requires_grad_(True)
+    ref = ol.axis_aligned_iou_loss(pa, pb, torch.from_numpy(w), avg_factor=321.0, loss_weight=0.7)
+    ref.backward()
+    ga = torch.from_numpy(a).cuda().requires_grad_(True); gb = torch.from_numpy(b).cuda().requires_grad_(True)
+    got = G.AxisAlignedIoULoss(loss_weight=0.7)(ga, gb, torch.from_numpy(w).cuda(), avg_factor=321.0)
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 1e-5 * abs(float(ref)) + 1e-7
+    for g, r in ((ga.grad, pa.grad), (gb.grad, pb.grad)):
+        assert np.allclose(g.cpu().numpy(), r.numpy(), rtol=1e-4, atol=1e-6 * float(r.abs().max()) + 1e-8)
+    # early-out: no positive weight
+    z = G.AxisAlignedIoULoss()(ga, gb, torch.zeros(500).cuda())
+    assert float(z) == 0.0 and z.requires_grad
