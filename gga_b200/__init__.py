@@ -8,6 +8,8 @@ from .ops import (points_in_boxes_all, points_in_boxes_bits, points_in_boxes_cpu
 from .project import box3d_project, pad_proj
 from .losses import (AxisAlignedIoULoss, GIoULoss, IoULoss, L1Loss, ProjectedGIoULoss, ProjectedIoULoss,
                      ProjectedL1Loss, axis_aligned_iou_loss, box2d_loss, projected_box_loss)
+from . import np_ops
+from .np_ops import face_distances, points_in_convex_polygon_3d_jit, points_in_frustm_indices, points_in_rbbox
 from .matching import convert_valid_bboxes_batch, image_box_overlap, match_dt_to_gt
 from .head import (boundary_projection_loss, get_distance_bev, get_prediction_single, gga_calculate_rotation,
                    pack_in_box_points, point_alignment_losses, point_box_distances)
@@ -16,7 +18,8 @@ __all__ = [
     'points_in_boxes_all', 'points_in_boxes_part', 'points_in_boxes_cpu', 'points_in_boxes_bits',
     'row_words', 'unpack_bits', 'box3d_project', 'pad_proj', 'box2d_loss', 'projected_box_loss',
     'ProjectedGIoULoss', 'ProjectedIoULoss', 'ProjectedL1Loss', 'GIoULoss', 'IoULoss', 'L1Loss',
-    'AxisAlignedIoULoss', 'axis_aligned_iou_loss',
+    'AxisAlignedIoULoss', 'axis_aligned_iou_loss', 'points_in_rbbox', 'points_in_convex_polygon_3d_jit',
+    'points_in_frustm_indices', 'face_distances', 'np_ops',
     'convert_valid_bboxes_batch', 'image_box_overlap', 'match_dt_to_gt', 'get_prediction_single',
     'gga_calculate_rotation', 'boundary_projection_loss', 'get_distance_bev', 'pack_in_box_points',
     'point_box_distances', 'point_alignment_losses',

@@ -58,6 +58,9 @@ SIGNATURES = {
     'gga_match_dt_gt': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p], c_int),
     'gga_image_box_overlap_f64': ([c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
+    'gga_points_in_convex_polygons': ([c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
+                                       c_void_p, c_void_p], c_int),
+    'gga_face_distances': ([c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p], c_int),
     'gga_pal_workspace_bytes': ([c_int, c_int], ctypes.c_size_t),
     'gga_point_box_alignment': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  ctypes.c_size_t, c_void_p], c_int),

@@ -202,6 +202,28 @@ int gga_image_box_overlap_f64(const double* boxes, int N, const double* query, i
                               int criterion, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Convex-polygon membership: _points_in_convex_polygon_3d_jit,
+ * /root/reference/mmdet3d/core/bbox/box_np_ops.py:641-675 — the test under points_in_rbbox
+ * (:353-376, the numpy/numba membership contract: ALL faces open, unlike the mmcv op) and under
+ * the frustum membership of tools/data_converter/utils_gga.py:88-101.
+ *   points : [N, pts_stride] float32 (points_f64 = 0) or float64, xyz first
+ *   normal : [M, S, 3], d : [M, S] plane coefficients from surface_equ_3d (:617-638), float32 or
+ *            float64 (planes_f64); arithmetic in the promoted type, left to right, unfused
+ *   num_surfaces : optional int64 [M] (the reference's quirk `k > num_surfaces[j]` is kept)
+ *   out    : uint8 [N, M], 1 = inside (n.p + d < 0 on every surface; NaN points are inside)
+ * ---------------------------------------------------------------------------------- */
+int gga_points_in_convex_polygons(const void* points, int pts_stride, int points_f64, const void* normal,
+                                  const void* d, int planes_f64, const int64_t* num_surfaces, int N, int M,
+                                  int S, uint8_t* out, void* stream);
+
+/* FCAF3DHead._get_face_distances, /root/reference/mmdet3d/models/dense_heads/fcaf3d_head.py:495-520,
+ * and its inside-box condition `min > 0` (:566-572).
+ *   points [N, 3], boxes [M, 7] = (gravity centre, dims, yaw) -> dist [N, M, 6] =
+ *   (dx_min, dx_max, dy_min, dy_max, dz_min, dz_max) and / or inside uint8 [N, M]. */
+int gga_face_distances(const float* points, const float* boxes, int N, int M, float* dist, uint8_t* inside,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Point-to-Box Alignment distances (the PAL loss inputs of GGA training) with their Jacobian.
  * Mirrors CenterHead_GGA.get_distance_single / get_distance_bev,
  * /root/reference/mmdet3d/models/dense_heads/centerpoint_head_gga.py:184-248 (called :692):

@@ -290,6 +290,75 @@ def main():
     hd['pal_cm'], hd['pal_cx'], hd['pal_cy'] = cm.numpy(), cx_.numpy(), cy_.numpy()
     hd['pal_grad_bev'] = bev.grad.numpy()
     np.savez_compressed(os.path.join(OUT, 'ref_head.npz'), **hd)
+
+    # --- convex-polygon membership family (contract a6 of SURVEY.md §8a and §8f rank 2):
+    #     box_np_ops.points_in_rbbox (:353-376) with float32 and float64 boxes, the frustum
+    #     membership of tools/data_converter/utils_gga.py:88-101, and FCAF3D's face distances
+    #     (fcaf3d_head.py:495-520, extracted from its source text like the head functions above)
+    cp = {}
+    nb = ref.box_np_ops
+    cb = kitti_like_boxes(rng, 24)
+    cb[:3, 6] = 0.0
+    cb[:3, :3] = np.round(cb[:3, :3] * 4) / 4
+    cb[:3, 3:6] = [4.0, 2.0, 1.5]
+    n_in = 1500
+    sel = rng.integers(0, 24, n_in)
+    loc = (rng.uniform(-0.6, 0.6, (n_in, 3)) * cb[sel, 3:6]).astype(np.float32)
+    cs, sn = np.cos(cb[sel, 6]), np.sin(cb[sel, 6])
+    pin = np.stack([cb[sel, 0] + loc[:, 0] * cs - loc[:, 1] * sn, cb[sel, 1] + loc[:, 0] * sn + loc[:, 1] * cs,
+                    cb[sel, 2] + cb[sel, 5] * 0.5 + loc[:, 2]], 1)
+    face = np.stack([cb[:3, 0] + 2.0, cb[:3, 1], cb[:3, 2] + 0.75], 1)            # exactly on a face: outside (open)
+    face2 = np.stack([cb[:3, 0], cb[:3, 1], cb[:3, 2]], 1)                         # on the bottom face: outside too
+    pout = np.stack([rng.uniform(0, 70, 600), rng.uniform(-40, 40, 600), rng.uniform(-3, 1, 600)], 1)
+    cpts = np.concatenate([pin, face, face2, pout], 0).astype(np.float32)
+    cpts4 = np.concatenate([cpts, rng.uniform(0, 1, (len(cpts), 1)).astype(np.float32)], 1)
+    cp['pts'], cp['boxes'] = cpts4, cb
+    cp['rbbox_f32'] = nb.points_in_rbbox(cpts4, cb)
+    cp['rbbox_f64boxes'] = nb.points_in_rbbox(cpts4, cb.astype(np.float64))
+    cp['rbbox_f64all'] = nb.points_in_rbbox(cpts4.astype(np.float64), cb.astype(np.float64))
+    camb = kitti_like_boxes(rng, 8)
+    cp['boxes_cam'] = camb
+    cp['rbbox_cam_axis1'] = nb.points_in_rbbox(cpts4, camb, z_axis=1, origin=(0.5, 1.0, 0.5))
+    surf = nb.corner_to_surfaces_3d(nb.center_to_corner_box3d(cb[:, :3], cb[:, 3:6], cb[:, 6], origin=(0.5, 0.5, 0), axis=2))
+    nv, dd = nb.surface_equ_3d(surf[:, :, :3, :])
+    cp['surfaces_f32'], cp['normal_f32'], cp['d_f32'] = surf, nv, dd
+    # frustum membership (utils_gga.points_in_frustm_indices)
+    ug = ref_loader._load('gga_tools_utils_gga', 'tools/data_converter/utils_gga.py')
+    fpts = np.stack([rng.uniform(0, 70, 4000), rng.uniform(-40, 40, 4000), rng.uniform(-3, 1, 4000),
+                     rng.uniform(0, 1, 4000)], 1).astype(np.float32)
+    rect64, trv64, p264 = RECT.astype(np.float64), TRV2C.astype(np.float64), P2.astype(np.float64)
+    bbs = np.array([[100.0, 120.0, 400.0, 300.0], [600.0, 150.0, 700.0, 250.0], [0.0, 0.0, 1242.0, 375.0]])
+    cp['fr_pts'], cp['fr_bboxes'] = fpts, bbs
+    cp['fr_rect'], cp['fr_Trv2c'], cp['fr_P2'] = rect64, trv64, p264
+    cp['fr_indices'] = np.stack([ug.points_in_frustm_indices(fpts, rect64, trv64, p264, bb)[:, 0] for bb in bbs], 1)
+    C_, R_, T_ = nb.projection_matrix_to_CRT_kitti(p264)
+    fr_surf = []
+    for bb in bbs:
+        fr = nb.get_frustum(bb.tolist(), C_)
+        fr -= T_
+        fr = np.linalg.inv(R_) @ fr.T
+        fr = nb.camera_to_lidar(fr.T, rect64, trv64)
+        fr_surf.append(nb.corner_to_surfaces_3d_jit(fr[np.newaxis, ...])[0])
+    cp['fr_surfaces'] = np.stack(fr_surf)
+    # FCAF3D face distances
+    import ast
+    import types as _types
+    fpath = os.path.join(ref_loader.REF_ROOT, 'mmdet3d/models/dense_heads/fcaf3d_head.py')
+    tree = ast.parse(open(fpath).read())
+    fn = [n for c in tree.body if isinstance(c, ast.ClassDef) and c.name == 'FCAF3DHead'
+          for n in c.body if isinstance(n, ast.FunctionDef) and n.name == '_get_face_distances'][0]
+    fn.decorator_list = []
+    glb = {'torch': torch, 'rotation_3d_in_axis': ref.rotation_3d_in_axis}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), fpath, 'exec'), glb)
+    fb = np.concatenate([rng.uniform(-4, 4, (12, 2)), rng.uniform(-1.5, 0.5, (12, 1)), rng.uniform(0.3, 2.5, (12, 3)),
+                         rng.uniform(-np.pi, np.pi, (12, 1))], 1).astype(np.float32)      # gravity centre boxes
+    fp = np.stack([rng.uniform(-5, 5, 900), rng.uniform(-5, 5, 900), rng.uniform(-2, 1, 900)], 1).astype(np.float32)
+    tpts = torch.from_numpy(fp).unsqueeze(1).expand(900, 12, 3)
+    tbox = torch.from_numpy(fb).expand(900, 12, 7)
+    fd = glb['_get_face_distances'](tpts, tbox)
+    cp['fd_pts'], cp['fd_boxes'], cp['fd_dist'] = fp, fb, fd.numpy()
+    cp['fd_inside'] = (fd.min(dim=-1).values > 0).numpy()
+    np.savez_compressed(os.path.join(OUT, 'ref_convex.npz'), **cp)
     print('wrote', sorted(os.listdir(OUT)))
 
 
