@@ -13,6 +13,7 @@ from .np_ops import face_distances, points_in_convex_polygon_3d_jit, points_in_f
 from .matching import convert_valid_bboxes_batch, image_box_overlap, match_dt_to_gt
 from .head import (boundary_projection_loss, get_distance_bev, get_prediction_single, gga_calculate_rotation,
                    pack_in_box_points, point_alignment_losses, point_box_distances)
+from .targets import get_targets, pack_targets, semantic_ratio_samples
 
 __all__ = [
     'points_in_boxes_all', 'points_in_boxes_part', 'points_in_boxes_cpu', 'points_in_boxes_bits',
@@ -22,6 +23,6 @@ __all__ = [
     'points_in_frustm_indices', 'face_distances', 'np_ops',
     'convert_valid_bboxes_batch', 'image_box_overlap', 'match_dt_to_gt', 'get_prediction_single',
     'gga_calculate_rotation', 'boundary_projection_loss', 'get_distance_bev', 'pack_in_box_points',
-    'point_box_distances', 'point_alignment_losses',
+    'point_box_distances', 'point_alignment_losses', 'get_targets', 'pack_targets', 'semantic_ratio_samples',
 ]
 __version__ = '0.1.0'

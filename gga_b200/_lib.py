@@ -32,6 +32,26 @@ class BoxLossArgs(ctypes.Structure):
     ]
 
 
+class TargetArgs(ctypes.Structure):
+    """Mirror of `gga_target_args` (include/gga_b200.h)."""
+    _fields_ = [
+        ('labels', c_void_p), ('frame_offsets', c_void_p), ('boxes_img', c_void_p), ('lidar2img', c_void_p),
+        ('pseudo', c_void_p), ('bdry', c_void_p), ('base_lidar2img', c_void_p), ('srl', c_void_p),
+        ('class_task', c_void_p), ('class_cls', c_void_p), ('task_channel0', c_void_p),
+        ('pseudo_dtype', ctypes.c_int32),
+        ('num_frames', ctypes.c_int32), ('n_tasks', ctypes.c_int32), ('n_classes', ctypes.c_int32),
+        ('n_channels', ctypes.c_int32), ('max_frame_objs', ctypes.c_int32), ('max_objs', ctypes.c_int32),
+        ('fm_w', ctypes.c_int32), ('fm_h', ctypes.c_int32), ('out_size_factor', ctypes.c_int32),
+        ('min_radius', ctypes.c_int32),
+        ('pc_x0', ctypes.c_float), ('pc_y0', ctypes.c_float), ('voxel_x', ctypes.c_float), ('voxel_y', ctypes.c_float),
+        ('gaussian_overlap', ctypes.c_double),
+        ('heatmap', c_void_p), ('anno_box', c_void_p), ('ind', c_void_p), ('mask', c_void_p),
+        ('anno_lidar2img', c_void_p), ('boundary_mask', c_void_p), ('src_index', c_void_p),
+    ]
+
+
+F32, F64 = 0, 1
+
 # every symbol include/gga_b200.h declares, with its argument types
 SIGNATURES = {
     'gga_version': ([], c_int),
@@ -64,6 +84,7 @@ SIGNATURES = {
     'gga_pal_workspace_bytes': ([c_int, c_int], ctypes.c_size_t),
     'gga_point_box_alignment': ([c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  ctypes.c_size_t, c_void_p], c_int),
+    'gga_pack_targets': ([ctypes.POINTER(TargetArgs), c_void_p], c_int),
     'gga_step_create': ([c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     'gga_step_destroy': ([c_void_p], c_int),
     'gga_step_run_host': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kBoxThreads) box_loss_kernel(const Args A) {
     float s = 0.f;
     for (unsigned int k = 0; k < gridDim.x; ++k) s += __ldcg(A.partial + k);
     *a.loss_sum = s;
-    if (a.loss_accum) *a.loss_accum += s;  // single writer: launches on one stream are ordered
+    if (a.loss_accum) atomicAdd(a.loss_accum, s);  // steps on different streams may share the accumulator
     *A.counter = 0u;
   }
 }

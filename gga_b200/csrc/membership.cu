@@ -870,8 +870,11 @@ __global__ void __launch_bounds__(NT, GSM ? 1 : kOcc) pib_stream_kernel(const St
 // tail paths: ~60 of its ~240 warp instructions per batch) disappears.  The SM is
 // instruction-issue bound in this kernel, so instructions are what is being saved.
 // ------------------------------------------------------------------------------------------
+// W: row words (8 / 16); the contract terms of the CTA's first frame sit in shared memory (T <= 512)
+template <int W>
 __global__ void __launch_bounds__(256, kOcc) pib_stream_fast_kernel(const StreamParams p) {
-  constexpr int W = 8, kW = 8;  // row words, warps per CTA
+  constexpr int kW = 8;         // warps per CTA
+  constexpr int kC = W / 4;     // 16-byte chunks of a row = store instructions per lane and batch
   extern __shared__ __align__(16) uint32_t smem_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bpf = p.batches_per_frame, stride = p.slots, T = p.num_boxes;
@@ -915,15 +918,15 @@ __global__ void __launch_bounds__(256, kOcc) pib_stream_fast_kernel(const Stream
       }
       wn = ld_u32(fc.grid + cell_of(v0.x, v0.y, fc));
     }
-    reinterpret_cast<uint4*>(stage)[lane] = make_uint4(0, 0, 0, 0);
-    reinterpret_cast<uint4*>(stage)[32 + lane] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < kC; ++k) reinterpret_cast<uint4*>(stage)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
     __syncwarp();
     for_each_hit(w, p, bf, prep_of(p, bf, f_smem, prep_smem), v.x, v.y, v.z,
                  [&](uint32_t t) { stage[lane * W + (t >> 5)] |= 1u << (t & 31u); });
     __syncwarp();
-    uint4* dst = reinterpret_cast<uint4*>(p.out) + (size_t)g * 64 + lane;
-    __stcs(dst, reinterpret_cast<const uint4*>(stage)[lane]);
-    __stcs(dst + 32, reinterpret_cast<const uint4*>(stage)[32 + lane]);
+    uint4* dst = reinterpret_cast<uint4*>(p.out) + (size_t)g * (8 * W) + lane;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) __stcs(dst + k * 32, reinterpret_cast<const uint4*>(stage)[k * 32 + lane]);
     __syncwarp();
     if (gn >= gend) break;
     g = gn;
@@ -1070,9 +1073,11 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   }
   if (g_tune_phase == 1) return GGA_OK;
 
-  if (mode == kModeBits && sp.vec4 && sp.row_words == 8 && sp.smem_prep && (num_points & 31) == 0 && !g_tune_nofast &&
-      kStreamThreads == 256) {
-    const size_t fsmem = (size_t)num_boxes * 32 + (size_t)8 * 32 * 4 * 8;
+  // lean variant: full 32-point batches, 8 / 16 row words, the frame's contract terms in shared memory
+  // (measured on B200: wider rows, whose terms stay in global memory, run faster in the generic kernel)
+  if (mode == kModeBits && sp.vec4 && (sp.row_words == 8 || sp.row_words == 16) && sp.smem_prep &&
+      (num_points & 31) == 0 && !g_tune_nofast && kStreamThreads == 256) {
+    const size_t fsmem = (size_t)num_boxes * 32 + (size_t)sp.row_words * 32 * 4 * 8;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(256);
@@ -1083,7 +1088,8 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_fast_kernel, sp));
+    if (sp.row_words == 8) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_fast_kernel<8>, sp));
+    else GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_fast_kernel<16>, sp));
     return GGA_OK;
   }
   {

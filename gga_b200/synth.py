@@ -174,3 +174,43 @@ def make_batch(cfg, frame0, n_frames, **kw):
         weight=np.stack([f['weight'] for f in fr]),
         gt2d=[f['gt2d'] for f in fr],
         img_hw=fr[0]['img_hw'])
+
+
+# ---------------------------------------------------------------------------------------------
+# target packing (CenterHead_GGA.get_targets_single inputs, centerpoint_head_gga.py:401-413)
+# ---------------------------------------------------------------------------------------------
+KITTI_TRAIN_CFG = dict(grid_size=[1408, 1600, 40], out_size_factor=8, voxel_size=[0.05, 0.05, 0.1],
+                       point_cloud_range=[0, -40, -3, 70.4, 40, 1], dense_reg=1, gaussian_overlap=0.1,
+                       max_objs=500, min_radius=2)      # configs/gga/gga_kitti_config.py:63-75
+KITTI_TASKS = [['Pedestrian'], ['Cyclist'], ['Car']]     # configs/gga/gga_kitti_config.py:39-43
+
+
+def make_target_frame(rng, n, n_classes=3, dtype=np.float64, adversarial=True):
+    """One frame of GGA annotations: labels int64 [n] (a few -1 = ignored), boxes_img [n,4],
+    lidar2img float32 [n,4,4] (per-object calib), pseudo `dtype` [n,7], bdry bool [n,4],
+    base lidar2img [4,4].  `adversarial` adds objects with degenerate extents and centres on /
+    outside the map borders (cell coordinate in (-1, 0), last cell, beyond)."""
+    boxes = make_boxes(rng, n).astype(np.float64) if n else np.zeros((0, 7))
+    boxes[:, 0:2] += rng.normal(0, 1e-3, (n, 2))
+    labels = rng.integers(0, n_classes, n).astype(np.int64)
+    if adversarial and n >= 12:
+        labels[rng.integers(0, n, 2)] = -1
+        boxes[0, 3] = 0.0                     # zero width: slot stays empty
+        boxes[1, 4] = -1.0                    # negative length
+        boxes[2, 0] = -0.2                    # cell coordinate in (-1, 0): truncates to cell 0
+        boxes[3, 0] = 70.39                   # last column
+        boxes[4, 1] = 39.99                   # last row
+        boxes[5, 0] = 70.41                   # one cell beyond
+        boxes[6, 1] = -40.5                   # below the map
+        boxes[7, 0:2] = (0.1, -39.9)          # corner: window clipped on two sides
+        boxes[8, 3:5] = (12.0, 30.0)          # very large object: radius >> min_radius
+        boxes[9, 3:5] = (0.05, 0.05)          # tiny: min_radius applies
+        boxes[10, 0:2] = (35.2, 0.0)          # exactly on a cell edge
+    l2i = kitti_lidar2img()
+    lidar2img = np.broadcast_to(l2i, (n, 4, 4)).copy()
+    lidar2img[::3, :3, 3] += rng.normal(0, 0.05, (len(range(0, n, 3)), 3)).astype(np.float32)
+    x1y1 = np.stack([rng.uniform(0, 1100, n), rng.uniform(0, 300, n)], 1)
+    boxes_img = np.concatenate([x1y1, x1y1 + rng.uniform(8, 200, (n, 2))], 1).astype(np.float32)
+    bdry = rng.random((n, 4)) < 0.15
+    return dict(labels=labels, boxes_img=boxes_img, lidar2img=lidar2img.astype(np.float32), pseudo=boxes.astype(dtype),
+                bdry=bdry, base_lidar2img=l2i)

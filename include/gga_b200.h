@@ -247,6 +247,68 @@ int gga_point_box_alignment(const float* points_xy, const int32_t* offsets, cons
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * GGA training-target packing — CenterHead_GGA.get_targets / get_targets_single,
+ * /root/reference/mmdet3d/models/dense_heads/centerpoint_head_gga.py:343-627, with
+ * gaussian_radius / draw_heatmap_gaussian of /root/reference/mmdet3d/core/utils/gaussian.py:6-86.
+ * One launch packs every frame and task (the reference: a Python loop over tasks x <= 500
+ * objects x frames of 0-dim tensor ops).  Objects of all frames are concatenated; frame f owns
+ * [frame_offsets[f], frame_offsets[f+1]).  Per task t the outputs are contiguous [F, max_objs, ...]
+ * blocks (task major), the layout get_targets builds with torch.stack (:377-397).
+ *   labels          int32 [n]       class index (gt_labels_3d); values outside [0, n_classes) match no task
+ *   boxes_img       float [n, 4]    2D labels (GGA_boxes_img)             -> anno_box[:, 0:4]
+ *   lidar2img       float [n, 16]   one 4x4 per object (GGA_lidar2img)    -> anno_lidar2img
+ *   pseudo          fp32 or fp64 [n, 7]  initial pseudo 3D boxes (GGA_init_pseudo_labels); the
+ *                   radius / centre arithmetic runs in this dtype, like torch's promotion of the
+ *                   0-dim operands in the reference (:546-572)
+ *   bdry            uint8 [n, 4]    GGA_bdry_masks (bool)                 -> boundary_mask = !bdry
+ *   base_lidar2img  float [F, 16]   img_meta['lidar2img'] (fills unused slots, :509-511)
+ *   srl             float [F, n_tasks]  the Semantic-Ratio sample of each (frame, task) (:515-527;
+ *                   the reference draws it with torch.normal — randomness stays with the caller)
+ *   class_task / class_cls  int32 [n_classes]  task of each class index and its index inside the task
+ *   task_channel0   int32 [n_tasks] first heatmap channel of each task (channels = classes, task order)
+ * outputs
+ *   heatmap         float [F, n_channels, fm_h, fm_w]   (zeroed by the call)
+ *   anno_box        float [n_tasks, F, max_objs, 5] = (x1, y1, x2, y2, srl)
+ *   ind             int64 [n_tasks, F, max_objs]   cy * fm_w + cx
+ *   mask            uint8 [n_tasks, F, max_objs]
+ *   anno_lidar2img  float [n_tasks, F, max_objs, 16]
+ *   boundary_mask   uint8 [n_tasks, F, max_objs, 4]  (4-byte aligned)
+ *   src_index       int32 [n_tasks, F, max_objs]   object (global index) placed in each slot, -1 = none:
+ *                   the order task_GGA_in_box_points lists the in-box point clusters in (:463-479)
+ * ---------------------------------------------------------------------------------- */
+#define GGA_F32 0
+#define GGA_F64 1
+typedef struct gga_target_args {
+  const int32_t* labels;
+  const int32_t* frame_offsets; /* [num_frames + 1] */
+  const float* boxes_img;
+  const float* lidar2img;
+  const void* pseudo;
+  const uint8_t* bdry;
+  const float* base_lidar2img;
+  const float* srl;
+  const int32_t* class_task;
+  const int32_t* class_cls;
+  const int32_t* task_channel0;
+  int32_t pseudo_dtype; /* GGA_F32 / GGA_F64 */
+  int32_t num_frames, n_tasks, n_classes, n_channels;
+  int32_t max_frame_objs; /* upper bound of objects per frame (<= 2048) */
+  int32_t max_objs;       /* train_cfg max_objs * dense_reg */
+  int32_t fm_w, fm_h;     /* grid_size[:2] // out_size_factor */
+  int32_t out_size_factor, min_radius;
+  float pc_x0, pc_y0, voxel_x, voxel_y; /* fp32, as the reference's torch.tensor(...) of the config lists */
+  double gaussian_overlap;
+  float* heatmap;
+  float* anno_box;
+  int64_t* ind;
+  uint8_t* mask;
+  float* anno_lidar2img;
+  uint8_t* boundary_mask;
+  int32_t* src_index;
+} gga_target_args;
+int gga_pack_targets(const gga_target_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * One training-shaped step from HOST buffers (the `points_in_boxes_cpu`-style contract of
  * /root/reference/mmdet3d/ops/__init__.py:12,38 extended to the whole loss step of
  * mmdet3d/models/dense_heads/centerpoint_head_gga.py:629-723): H2D copies, membership masks,

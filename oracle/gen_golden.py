@@ -359,8 +359,60 @@ def main():
     cp['fd_pts'], cp['fd_boxes'], cp['fd_dist'] = fp, fb, fd.numpy()
     cp['fd_inside'] = (fd.min(dim=-1).values > 0).numpy()
     np.savez_compressed(os.path.join(OUT, 'ref_convex.npz'), **cp)
+    gen_targets()
     print('wrote', sorted(os.listdir(OUT)))
 
 
+TARGET_CASES = (
+    # name, class_names, train_cfg overrides, objects per frame, pseudo dtype
+    ('kitti64', [['Pedestrian'], ['Cyclist'], ['Car']], {}, (40, 0, 15, 3), np.float64),
+    ('kitti32', [['Pedestrian'], ['Cyclist'], ['Car']], {}, (33, 12), np.float32),
+    ('multi64', [['a', 'b'], ['c'], ['d', 'e', 'f']], dict(max_objs=6, min_radius=1, gaussian_overlap=0.3), (50, 21),
+     np.float64),
+    ('multi32', [['a', 'b', 'c'], ['d']], dict(max_objs=9, dense_reg=2, out_size_factor=4, gaussian_overlap=0.5),
+     (60, 14, 0), np.float32),
+)
+
+
+def gen_targets():
+    """tests/golden/ref_targets.npz: the reference's own get_targets_single (source text executed
+    by ref_loader.load_target_functions) on synthetic GGA annotations — KITTI tasks and multi-class
+    tasks, fp64 and fp32 pseudo labels, slots beyond max_objs, degenerate and border objects."""
+    import types
+    from gga_b200 import synth
+    from gga_b200.targets import semantic_ratio_samples
+    g = {}
+    for name, class_names, over, counts, dt in TARGET_CASES:
+        cfg = dict(synth.KITTI_TRAIN_CFG, **over)
+        fn = ref_loader.load_target_functions(cfg, class_names)
+        rng = np.random.default_rng(sum(map(ord, name)))
+        n_classes = sum(len(c) for c in class_names)
+        for f, n in enumerate(counts):
+            fr = synth.make_target_frame(rng, n, n_classes, dt)
+            for k, v in fr.items():
+                g[f'{name}_f{f}_{k}'] = v
+            gt = types.SimpleNamespace(gravity_center=torch.zeros((n, 3)), tensor=torch.zeros((n, 7)))
+            ibp = [torch.full((1 + i % 3, 4), float(i), dtype=torch.float64) for i in range(n)]
+            torch.manual_seed(1000 + f)
+            g[f'{name}_f{f}_srl'] = semantic_ratio_samples(1, len(class_names))[0].numpy()
+            torch.manual_seed(1000 + f)
+            out = fn(gt, torch.from_numpy(fr['labels']), torch.from_numpy(fr['boxes_img']),
+                     torch.from_numpy(fr['lidar2img']), torch.from_numpy(fr['pseudo']), torch.from_numpy(fr['bdry']),
+                     ibp, dict(lidar2img=fr['base_lidar2img']))
+            heat, anno, ind, mask, l2i, tibp, bm = out
+            for t in range(len(class_names)):
+                g[f'{name}_f{f}_t{t}_heatmap'] = heat[t].numpy()
+                g[f'{name}_f{f}_t{t}_anno_box'] = anno[t].numpy()
+                g[f'{name}_f{f}_t{t}_ind'] = ind[t].numpy()
+                g[f'{name}_f{f}_t{t}_mask'] = mask[t].numpy()
+                g[f'{name}_f{f}_t{t}_lidar2img'] = l2i[t].numpy()
+                g[f'{name}_f{f}_t{t}_bmask'] = bm[t].numpy()
+                g[f'{name}_f{f}_t{t}_ibp_order'] = np.asarray([int(p[0, 0]) for p in tibp[t]], np.int32)
+    np.savez_compressed(os.path.join(OUT, 'ref_targets.npz'), **g)
+
+
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] == ['targets']:
+        gen_targets()
+    else:
+        main()

@@ -177,3 +177,29 @@ def load_head_functions(train_cfg, norm_bbox=True):
         setattr(self, name, types.MethodType(glb[name], self))
         setattr(out, name, getattr(self, name))
     return out
+
+
+def load_target_functions(train_cfg, class_names):
+    """The reference's OWN ``CenterHead_GGA.get_targets_single`` (centerpoint_head_gga.py:401-627),
+    its source text executed unmodified against a stand-in ``self``, with the reference's own
+    ``draw_heatmap_gaussian`` / ``gaussian_radius`` (mmdet3d/core/utils/gaussian.py, loaded from
+    its file: it only needs numpy and torch).  Returns the bound method."""
+    import ast
+    import importlib.util
+    import numpy as np
+    import torch
+    gpath = os.path.join(REF_ROOT, 'mmdet3d/core/utils/gaussian.py')
+    spec = importlib.util.spec_from_file_location('_ref_gaussian', gpath)
+    gmod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gmod)
+    path = os.path.join(REF_ROOT, 'mmdet3d/models/dense_heads/centerpoint_head_gga.py')
+    tree = ast.parse(open(path).read(), filename=path)
+    funcs = [n for cls in tree.body if isinstance(cls, ast.ClassDef) and cls.name == 'CenterHead_GGA'
+             for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == 'get_targets_single']
+    assert len(funcs) == 1
+    glb = {'torch': torch, 'np': np, 'draw_heatmap_gaussian': gmod.draw_heatmap_gaussian,
+           'gaussian_radius': gmod.gaussian_radius, '__builtins__': __builtins__}
+    exec(compile(ast.Module(body=funcs, type_ignores=[]), path, 'exec'), glb)
+    self = types.SimpleNamespace(train_cfg=train_cfg, class_names=class_names, task_heads=[None] * len(class_names),
+                                 with_velocity=False)
+    return types.MethodType(glb['get_targets_single'], self)

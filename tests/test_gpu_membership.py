@@ -121,7 +121,8 @@ def test_camera_golden_through_coordinate_conversion():
 
 
 @pytest.mark.parametrize('M,T', [(1, 1), (31, 7), (1000, 32), (1025, 33), (4097, 64), (3000, 65), (2048, 128),
-                                 (5000, 129), (7777, 256), (3001, 257), (2000, 700), (1500, 1024), (600, 1500)])
+                                 (5000, 129), (7777, 256), (3001, 257), (2000, 700), (1500, 1024), (600, 1500),
+                                 (4096, 300), (8192, 512), (2048, 513), (2016, 768), (6400, 1024)])
 def test_random_shapes_bit_exact(M, T):
     rng = np.random.default_rng(M * 31 + T)
     boxes = synth.make_boxes(rng, T)
@@ -199,6 +200,26 @@ def test_points_in_boxes_cpu_signature_host_tensors():
     out = G.points_in_boxes_cpu(p, b)
     assert not out.is_cuda and out.dtype == torch.int32 and tuple(out.shape) == (1, 20000, 64)
     assert np.array_equal(out[0].numpy(), om.points_in_boxes_all_np(f['points'], f['boxes'], 8))
+
+
+@pytest.mark.parametrize('T,frames,M', [(200, 3, 4000), (256, 5, 4096), (400, 3, 2048), (512, 2, 4128),
+                                        (700, 3, 2080), (1024, 2, 3200), (1024, 3, 999)])
+def test_multi_frame_bits_lean_widths(T, frames, M):
+    """[F, N, 4] points, every row width of the lean stream variants (8/16/24/32 words), frames
+    with different boxes in one call."""
+    rng = np.random.default_rng(T * 7 + frames)
+    bx, px = [], []
+    for f in range(frames):
+        b = synth.make_boxes(rng, T)
+        b[:, 6] = rng.uniform(-7, 7, T)
+        bx.append(b)
+        px.append(synth.make_points(rng, M, b, sort_azimuth=bool(f % 2)))
+    bits = G.points_in_boxes_bits(cu(np.stack(px)), cu(np.stack(bx)))
+    ub = G.unpack_bits(bits, T).cpu().numpy()
+    for f in range(frames):
+        ref = om.points_in_boxes_all_np(px[f][:, :3], bx[f], nthreads=8)
+        assert np.array_equal(ub[f], ref), f
+        assert ref.any()
 
 
 @pytest.mark.parametrize('cfg,frames', [(1, 1), (2, 2), (3, 1)])

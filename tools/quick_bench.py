@@ -35,13 +35,15 @@ def main():
     ap.add_argument('--grids', default='0,8,16,24,32,40,48,64')
     ap.add_argument('--ctas', default='0')
     ap.add_argument('--phase', type=int, default=0)
+    ap.add_argument('--N', type=int, default=0)
+    ap.add_argument('--M', type=int, default=0)
     a = ap.parse_args()
     c = synth.CONFIGS[a.cfg]
     pool = []
     for k in range(a.pool):
-        bt = synth.make_batch(a.cfg, k * a.frames, a.frames, sort_azimuth=not a.unsorted)
+        bt = synth.make_batch(a.cfg, k * a.frames, a.frames, sort_azimuth=not a.unsorted, N=a.N or None, M=a.M or None)
         pool.append((torch.from_numpy(bt['points']).cuda(), torch.from_numpy(bt['boxes']).cuda()))
-    N, M = c['N'], c['M']
+    N, M = a.N or c['N'], a.M or c['M']
     W = G.row_words(M)
     outs = [torch.empty((a.frames, N, W), dtype=torch.int32, device='cuda') for _ in range(a.pool)]
     bytes_step = a.frames * (16 * N + 28 * M + 4 * N * W)
@@ -71,7 +73,7 @@ def main():
                     call(k)
             ms = time_ms(g_.replay, iters=10, warm=2) / reps
             L.gga_test_pib_phase(0)
-            r = dict(cfg=a.cfg, phase=a.phase, grid=g, ctas=ct, ms=round(ms, 4), gbs=round(bytes_step / ms / 1e6, 1),
+            r = dict(cfg=a.cfg, N=N, M=M, phase=a.phase, grid=g, ctas=ct, ms=round(ms, 4), gbs=round(bytes_step / ms / 1e6, 1),
                      frames_per_s=round(a.frames / ms * 1e3, 1))
             print(json.dumps(r), flush=True)
             res.append(r)
