@@ -431,7 +431,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-streams', type=int, default=3)
-    ap.add_argument('--lanes', type=int, default=2, help='independent steps in flight on one GPU (parallel graph branches)')
+    ap.add_argument('--lanes', type=int, default=6, help='independent steps in flight on one GPU (parallel graph branches)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

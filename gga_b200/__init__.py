@@ -14,6 +14,7 @@ from .matching import convert_valid_bboxes_batch, image_box_overlap, match_dt_to
 from .head import (boundary_projection_loss, get_distance_bev, get_prediction_single, gga_calculate_rotation,
                    pack_in_box_points, point_alignment_losses, point_box_distances)
 from .targets import get_targets, pack_targets, semantic_ratio_samples
+from .kitti_format import bbox2result_kitti, kitti_lines, pseudo_label_matching_kitti
 
 __all__ = [
     'points_in_boxes_all', 'points_in_boxes_part', 'points_in_boxes_cpu', 'points_in_boxes_bits',
@@ -24,5 +25,6 @@ __all__ = [
     'convert_valid_bboxes_batch', 'image_box_overlap', 'match_dt_to_gt', 'get_prediction_single',
     'gga_calculate_rotation', 'boundary_projection_loss', 'get_distance_bev', 'pack_in_box_points',
     'point_box_distances', 'point_alignment_losses', 'get_targets', 'pack_targets', 'semantic_ratio_samples',
+    'bbox2result_kitti', 'kitti_lines', 'pseudo_label_matching_kitti',
 ]
 __version__ = '0.1.0'

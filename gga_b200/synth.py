@@ -214,3 +214,48 @@ def make_target_frame(rng, n, n_classes=3, dtype=np.float64, adversarial=True):
     bdry = rng.random((n, 4)) < 0.15
     return dict(labels=labels, boxes_img=boxes_img, lidar2img=lidar2img.astype(np.float32), pseudo=boxes.astype(dtype),
                 bdry=bdry, base_lidar2img=l2i)
+
+
+def make_detection_frames(seed, counts, gts=6):
+    """Synthetic inputs of the result-formatting / pseudo-label rewrite step: per frame a KITTI
+    info dict (calib float64 4x4 like the info pkls, image idx / shape, annos with GGA fields and
+    trailing DontCare objects) and a detection dict (boxes_3d [n, 7] LiDAR bottom-centre boxes, some
+    outside the image / range, scores_3d, labels_3d)."""
+    rng = np.random.default_rng(seed)
+    infos, dets = [], []
+    names = np.array(['Pedestrian', 'Cyclist', 'Car'])
+    for f, n in enumerate(counts):
+        P2 = KITTI_P2.astype(np.float64).copy()
+        P2[0, 3] += rng.normal(0, 1.0)
+        calib = dict(R0_rect=KITTI_RECT.astype(np.float64), Tr_velo_to_cam=KITTI_TRV2C.astype(np.float64), P2=P2)
+        boxes = make_boxes(rng, n).astype(np.float32) if n else np.zeros((0, 7), np.float32)
+        boxes[:, 6] = rng.uniform(-7, 7, n)
+        if n >= 6:
+            boxes[0, 0] = -5.0          # behind the sensor: outside the range and the image
+            boxes[1, 1] = 45.0          # outside the point-cloud range
+            boxes[2, 0:2] = (3.0, 9.0)  # in range, projects left of the image
+            boxes[3, 0:2] = (6.0, -2.0) # close: box clipped by the image borders
+        g = min(gts, max(n, 1)) + 2
+        gb = (boxes[rng.integers(0, max(n, 1), g)] if n else make_boxes(rng, g)).copy()
+        gb[:, :3] += rng.normal(0, 0.3, (g, 3)).astype(np.float32)
+        bbox = _project_kitti_cam_np(gb).astype(np.float64)
+        bbox[:, [0, 2]] = np.clip(bbox[:, [0, 2]], 0, 1242)
+        bbox[:, [1, 3]] = np.clip(bbox[:, [1, 3]], 0, 375)
+        gname = names[rng.integers(0, 3, g)].astype('<U10')
+        gname[-2:] = 'DontCare'
+        if g > 4:
+            gname[1] = 'Van'            # a class the matching drops
+        annos = dict(name=gname, bbox=bbox, truncated=rng.uniform(0, 1, g), occluded=rng.integers(0, 3, g),
+                     alpha=rng.uniform(-3, 3, g), dimensions=rng.uniform(0.5, 4, (g, 3)),
+                     location=rng.uniform(-10, 40, (g, 3)), rotation_y=rng.uniform(-3, 3, g),
+                     index=np.arange(g, dtype=np.int32), group_ids=np.arange(g, dtype=np.int32),
+                     difficulty=rng.integers(-1, 3, g).astype(np.int32),
+                     num_points_in_gt=rng.integers(0, 400, g).astype(np.int32),
+                     GGA_init_pseudo_label=rng.uniform(-1, 1, (g, 7)), GGA_boxes_img=bbox.copy(),
+                     GGA_bdry_masks=rng.random((g, 4)) < 0.2,
+                     GGA_in_box_points=[np.ones((1 + i, 4)) for i in range(g)])
+        infos.append(dict(image=dict(image_idx=100 + 7 * f, image_shape=np.array([375, 1242], np.int32)), calib=calib,
+                          annos=annos))
+        dets.append(dict(boxes_3d=boxes, scores_3d=rng.uniform(0.05, 1, n).astype(np.float32),
+                         labels_3d=rng.integers(0, 3, n).astype(np.int64)))
+    return infos, dets

@@ -32,10 +32,6 @@ def semantic_ratio_samples(num_frames, n_tasks):
     return out
 
 
-def _as_list(x, n):
-    return list(x) if isinstance(x, (list, tuple)) else [x[i] for i in range(n)]
-
-
 class PackedTargets:
     """Raw task-major outputs of one ``gga_pack_targets`` launch (see include/gga_b200.h)."""
 
@@ -75,16 +71,15 @@ def pack_targets(labels, frame_offsets, boxes_img, lidar2img, pseudo, bdry, base
     pdt = pseudo.dtype if pseudo.dtype in (torch.float32, torch.float64) else torch.float32
 
     def dv(x, dtype):
-        return torch.as_tensor(x).to(device=dev, dtype=dtype).contiguous()
+        x = torch.as_tensor(x).to(device=dev, dtype=dtype).contiguous()
+        return x if x.numel() else torch.zeros((16,), dtype=dtype, device=dev)   # the C ABI takes no null pointers
 
     t_lab = dv(labels, torch.int32)
     t_fo = fo.to(dev)
-    t_img = dv(boxes_img, torch.float32).reshape(n, 4)
-    t_l2i = dv(lidar2img, torch.float32).reshape(n, 16)
-    t_ps = dv(pseudo, pdt).reshape(n, 7)
-    t_bd = dv(bdry, torch.uint8).reshape(n, 4)
-    t_base = dv(base_lidar2img, torch.float32).reshape(F, 16)
-    t_srl = dv(srl, torch.float32).reshape(F, n_tasks)
+    t_img, t_l2i, t_ps = dv(boxes_img, torch.float32), dv(lidar2img, torch.float32), dv(pseudo, pdt)
+    t_bd, t_base, t_srl = dv(bdry, torch.uint8), dv(base_lidar2img, torch.float32), dv(srl, torch.float32)
+    assert n == 0 or (t_img.numel() == 4 * n and t_l2i.numel() == 16 * n and t_ps.numel() == 7 * n and t_bd.numel() == 4 * n)
+    assert F == 0 or (t_base.numel() == 16 * F and t_srl.numel() == F * n_tasks)
     t_ct, t_cc, t_c0 = dv(class_task, torch.int32), dv(class_cls, torch.int32), dv(chan0, torch.int32)
 
     heatmap = torch.empty((F, n_classes, fm_h, fm_w), dtype=torch.float32, device=dev)

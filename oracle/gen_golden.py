@@ -360,6 +360,7 @@ def main():
     cp['fd_inside'] = (fd.min(dim=-1).values > 0).numpy()
     np.savez_compressed(os.path.join(OUT, 'ref_convex.npz'), **cp)
     gen_targets()
+    gen_format()
     print('wrote', sorted(os.listdir(OUT)))
 
 
@@ -411,8 +412,49 @@ def gen_targets():
     np.savez_compressed(os.path.join(OUT, 'ref_targets.npz'), **g)
 
 
+FORMAT_COUNTS = (24, 0, 7, 2, 40)
+FORMAT_CLASSES = ['Pedestrian', 'Cyclist', 'Car']
+ANNO_KEYS = ('name', 'truncated', 'occluded', 'alpha', 'bbox', 'dimensions', 'location', 'rotation_y', 'score',
+             'sample_idx')
+
+
+def gen_format():
+    """tests/golden/ref_format.npz: the reference's own bbox2result_kitti / convert_valid_bboxes
+    (kitti_dataset_GGA_match.py:458-571, 685-765) and pseudo_label_matching_kitti
+    (tools/utils_pseudo_labels_gga.py:17-88), source text executed through
+    ref_loader.load_format_functions on synthetic detections."""
+    import copy
+    import tempfile
+    from gga_b200 import synth
+    infos, dets = synth.make_detection_frames(2024, FORMAT_COUNTS)
+    R = ref_loader.load_format_functions(infos, list(synth.KITTI_MATCH_RANGE))
+    net = [dict(boxes_3d=R.LiDARInstance3DBoxes(torch.from_numpy(d['boxes_3d']).clone()),
+                scores_3d=torch.from_numpy(d['scores_3d']), labels_3d=torch.from_numpy(d['labels_3d'])) for d in dets]
+    g = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        annos = R.bbox2result_kitti(net, FORMAT_CLASSES, submission_prefix=tmp)
+        for f, a in enumerate(annos):
+            for k in ANNO_KEYS:
+                g[f'f{f}_{k}'] = np.asarray(a[k])
+            g[f'f{f}_txt'] = np.array(open(os.path.join(tmp, f"{infos[f]['image']['image_idx']:06d}.txt")).read())
+    gt_infos = copy.deepcopy(infos)
+    # frames without detections keep their annotations' keys but no rows (:52-57); frame 3 may lose
+    # every detection to the validity test
+    cleaned = R.pseudo_label_matching_kitti(gt_infos, copy.deepcopy(annos))
+    (path, new_infos), = R.dumped
+    for f in range(len(infos)):
+        for k, v in new_infos[f]['annos'].items():
+            g[f'f{f}_new_{k}'] = np.asarray(v)
+        for k, v in cleaned[f].items():
+            g[f'f{f}_clean_{k}'] = np.asarray(v)
+    g['dump_path'] = np.array(path)
+    np.savez_compressed(os.path.join(OUT, 'ref_format.npz'), **g)
+
+
 if __name__ == '__main__':
     if sys.argv[1:] == ['targets']:
         gen_targets()
+    elif sys.argv[1:] == ['format']:
+        gen_format()
     else:
         main()

@@ -203,3 +203,44 @@ def load_target_functions(train_cfg, class_names):
     self = types.SimpleNamespace(train_cfg=train_cfg, class_names=class_names, task_heads=[None] * len(class_names),
                                  with_velocity=False)
     return types.MethodType(glb['get_targets_single'], self)
+
+
+def load_format_functions(data_infos, pcd_limit_range):
+    """The reference's OWN ``KittiDataset_GGA_match.bbox2result_kitti`` (:458-571) and
+    ``convert_valid_bboxes`` (:685-765), plus ``pseudo_label_matching_kitti``
+    (tools/utils_pseudo_labels_gga.py:17-88): source text executed unmodified against a stand-in
+    ``self`` (the dataset module needs the mmdet registries).  ``mmcv`` is a stub with
+    ``mkdir_or_exist`` / ``track_iter_progress`` / ``dump`` (dump keeps the object in
+    ``ns.dumped``).  Returns a namespace (bbox2result_kitti, pseudo_label_matching_kitti, dumped)."""
+    import ast
+    import copy
+    import numpy as np
+    import torch
+    ns = load_reference()
+    out = types.SimpleNamespace(dumped=[])
+    mm = types.SimpleNamespace(mkdir_or_exist=lambda d: os.makedirs(d, exist_ok=True),
+                               track_iter_progress=lambda it: it,
+                               dump=lambda obj, path: out.dumped.append((path, obj)))
+    path = os.path.join(REF_ROOT, 'mmdet3d/datasets/kitti_dataset_GGA_match.py')
+    tree = ast.parse(open(path).read(), filename=path)
+    wanted = {'bbox2result_kitti', 'convert_valid_bboxes'}
+    funcs = [n for cls in tree.body if isinstance(cls, ast.ClassDef) and cls.name == 'KittiDataset_GGA_match'
+             for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {f.name for f in funcs} == wanted
+    glb = {'torch': torch, 'np': np, 'mmcv': mm, 'Box3DMode': ns.Box3DMode, 'points_cam2img': ns.points_cam2img,
+           '__builtins__': __builtins__}
+    exec(compile(ast.Module(body=funcs, type_ignores=[]), path, 'exec'), glb)
+    self = types.SimpleNamespace(data_infos=data_infos, pcd_limit_range=pcd_limit_range)
+    for name in wanted:
+        setattr(self, name, types.MethodType(glb[name], self))
+    out.bbox2result_kitti = self.bbox2result_kitti
+    path2 = os.path.join(REF_ROOT, 'tools/utils_pseudo_labels_gga.py')
+    tree2 = ast.parse(open(path2).read(), filename=path2)
+    funcs2 = [n for n in tree2.body if isinstance(n, ast.FunctionDef)
+              and n.name in ('drop_arrays_by_name', 'pseudo_label_matching_kitti')]
+    glb2 = {'np': np, 'copy': copy, 'mmcv': mm, 'get_split_parts': ns.kitti_eval.get_split_parts,
+            'calculate_iou_partly': ns.kitti_eval.calculate_iou_partly, '__builtins__': __builtins__}
+    exec(compile(ast.Module(body=funcs2, type_ignores=[]), path2, 'exec'), glb2)
+    out.pseudo_label_matching_kitti = glb2['pseudo_label_matching_kitti']
+    out.LiDARInstance3DBoxes = ns.LiDARInstance3DBoxes
+    return out
