@@ -565,6 +565,7 @@ struct StreamParams {
   int smem_prep;          // the CTA keeps the contract terms of one frame in shared memory
   int dynamic;            // CTA-local dynamic batch draws instead of static strides (experiment; default off)
   int grid_smem_words;    // GSM variant: words of the frame's cell grid copied to shared memory
+  int rf;                 // frame-local variant: ranges per frame (R = rf * frames, tb_base / tb_rem per frame)
   unsigned long long* trace;  // profiling hook: 16 globaltimer stamps per warp (NULL = off)
 };
 
@@ -863,70 +864,72 @@ __global__ void __launch_bounds__(NT, GSM ? 1 : kOcc) pib_stream_kernel(const St
 }
 
 // ------------------------------------------------------------------------------------------
-// stream kernel, lean variant for the training shapes: bit-packed rows of 8 words (129..256
-// boxes), 16-byte points, N a multiple of 32.  Then batch g of the frame-major list is simply
-// points[32 g .. 32 g + 31] and rows out[256 g ..], every batch is full and aligned, and the
-// per-batch bookkeeping of the general kernel (frame decode, partial batches, alignment and
-// tail paths: ~60 of its ~240 warp instructions per batch) disappears.  The SM is
-// instruction-issue bound in this kernel, so instructions are what is being saved.
+// stream kernel, lean variant for the training shapes: bit-packed rows of 8 / 16 words (129..512
+// boxes), 16-byte points.  Batch g of a frame is points[32 g .. 32 g + 31] and rows
+// out[32 g ..] (16-byte aligned because rows are multiples of 16 bytes), and the per-batch
+// bookkeeping of the general kernel (frame decode, alignment and tail paths: ~60 of its ~240
+// warp instructions per batch) disappears.  The SM is instruction-issue bound in this kernel,
+// so instructions are what is being saved.
 // ------------------------------------------------------------------------------------------
-// W: row words (8 / 16); the contract terms of the CTA's first frame sit in shared memory (T <= 512)
-template <int W>
-__global__ void __launch_bounds__(256, kOcc) pib_stream_fast_kernel(const StreamParams p) {
-  constexpr int kW = 8;         // warps per CTA (4-warp CTAs measured: no gain)
-  constexpr int kC = W / 4;     // 16-byte chunks of a row = store instructions per lane and batch
+// Frame-local ranges: every range lies inside one frame (R = rf ranges per frame x frames), so a
+// CTA serves exactly one frame — its contract terms are always the shared-memory copy (LDS, no
+// generic-pointer select per candidate), the frame header and grid pointer are loop invariant and
+// the frame-crossing bookkeeping of the loop disappears.
+// FULL: N is a multiple of 32 (every batch has 32 points); otherwise the last batch of a frame is
+// ragged: its loads are clamped to the frame's last point and its surplus rows are not stored.
+template <int W, bool FULL>
+__global__ void __launch_bounds__(256, kOcc) pib_stream_frame_kernel(const StreamParams p) {
+  constexpr int kW = 8;      // warps per CTA
+  constexpr int kC = W / 4;  // 16-byte chunks of a row = store instructions per lane and batch
   extern __shared__ __align__(16) uint32_t smem_all[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int bpf = p.batches_per_frame, stride = p.slots, T = p.num_boxes;
+  const int stride = p.slots, T = p.num_boxes, N = p.num_points;
   const float4* prep_smem = reinterpret_cast<const float4*>(smem_all);
   uint32_t* stage = smem_all + 8 * T + warp * (32 * W);
 
   const int r = blockIdx.x % p.R, cta = (int)(blockIdx.x / p.R);
-  const int g0 = r * p.tb_base + min(r, p.tb_rem);
-  const int gend = g0 + p.tb_base + (r < p.tb_rem ? 1 : 0);
-  const int f_smem = min(p.num_frames - 1, (g0 + cta * kW) / bpf);  // frame whose contract terms sit in smem
-  int g = g0 + cta * kW + warp;                                     // this warp's batches: g, g + stride, ...
-  const float4* pts = reinterpret_cast<const float4*>(p.points) + lane;
+  const int f = r / p.rf, rr = r - f * p.rf;
+  const int g0 = rr * p.tb_base + min(rr, p.tb_rem);  // batches of this range, frame-local numbering
+  const int gend = g0 + p.tb_base + (rr < p.tb_rem ? 1 : 0);
+  int g = g0 + cta * kW + warp;                       // this warp's batches: g, g + stride, ...
+  const float4* pts = reinterpret_cast<const float4*>(p.points) + (size_t)f * N;
+  uint4* rows = reinterpret_cast<uint4*>(p.out) + (size_t)f * N * kC;
+  auto load_pt = [&](int gb) { return __ldcs(pts + (FULL ? gb * 32 + lane : min(gb * 32 + lane, N - 1))); };
   float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-  if (g < gend) v0 = __ldcs(pts + (size_t)g * 32);
-  if (g + stride < gend) v1 = __ldcs(pts + (size_t)(g + stride) * 32);
+  if (g < gend) v0 = load_pt(g);
+  if (g + stride < gend) v1 = load_pt(g + stride);
 
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the prep kernel wrote
   {
-    const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f_smem * 2 * T;
+    const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f * 2 * T;
     float4* dst = reinterpret_cast<float4*>(smem_all);
     for (int k = threadIdx.x; k < 2 * T; k += 256) dst[k] = ld_f4(src + k);
   }
   __syncthreads();
   if (g >= gend) return;
 
-  int f = g / bpf, fend = (f + 1) * bpf;  // frame of the batch whose cell word is being requested
-  FrameCtx fc = load_frame(p, f);
+  const FrameCtx fc = load_frame(p, f);
   uint32_t wn = ld_u32(fc.grid + cell_of(v0.x, v0.y, fc));
 #pragma unroll 1
   for (;;) {
     const float4 v = v0;
     const uint32_t w = wn;
-    const int bf = f, gn = g + stride;
+    const int gn = g + stride;
     // rotate: points of batch g + 2 stride, cell word of batch g + stride
     v0 = v1;
-    if (gn + stride < gend) v1 = __ldcs(pts + (size_t)(gn + stride) * 32);
-    if (gn < gend) {
-      if (gn >= fend) {
-        do { ++f; fend += bpf; } while (gn >= fend);
-        fc = load_frame(p, f);
-      }
-      wn = ld_u32(fc.grid + cell_of(v0.x, v0.y, fc));
-    }
+    if (gn + stride < gend) v1 = load_pt(gn + stride);
+    if (gn < gend) wn = ld_u32(fc.grid + cell_of(v0.x, v0.y, fc));
 #pragma unroll
     for (int k = 0; k < kC; ++k) reinterpret_cast<uint4*>(stage)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
     __syncwarp();
-    for_each_hit(w, p, bf, prep_of(p, bf, f_smem, prep_smem), v.x, v.y, v.z,
+    for_each_hit(w, p, f, prep_smem, v.x, v.y, v.z,
                  [&](uint32_t t) { stage[lane * W + (t >> 5)] |= 1u << (t & 31u); });
     __syncwarp();
-    uint4* dst = reinterpret_cast<uint4*>(p.out) + (size_t)g * (8 * W) + lane;
+    uint4* dst = rows + (size_t)g * (32 * kC) + lane;
+    const int lim = FULL ? 32 * kC : min(32, N - g * 32) * kC;  // 16-byte chunks of the batch's rows
 #pragma unroll
-    for (int k = 0; k < kC; ++k) __stcs(dst + k * 32, reinterpret_cast<const uint4*>(stage)[k * 32 + lane]);
+    for (int k = 0; k < kC; ++k)
+      if (FULL || k * 32 + lane < lim) __stcs(dst + k * 32, reinterpret_cast<const uint4*>(stage)[k * 32 + lane]);
     __syncwarp();
     if (gn >= gend) break;
     g = gn;
@@ -1030,6 +1033,7 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   sp.tb_base = (int)(tb / R);
   sp.tb_rem = (int)(tb % R);
   sp.dynamic = 0;
+  sp.rf = 0;
   GGA_REQUIRE(sp.R <= kMaxRanges, "too many ranges");
   sp.vec4 = (pts_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0) ? 1 : 0;
   const int grid = (int)R * occ;
@@ -1081,7 +1085,7 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   // lean variant: full 32-point batches, 8 / 16 row words, the frame's contract terms in shared memory
   // (measured on B200: wider rows, whose terms stay in global memory, run faster in the generic kernel)
   if (mode == kModeBits && sp.vec4 && (sp.row_words == 8 || sp.row_words == 16) && sp.smem_prep &&
-      (num_points & 31) == 0 && !g_tune_nofast && kStreamThreads == 256) {
+      !g_tune_nofast && kStreamThreads == 256) {
     const size_t fsmem = (size_t)num_boxes * 32 + (size_t)sp.row_words * 32 * 4 * 8;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -1093,8 +1097,22 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (sp.row_words == 8) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_fast_kernel<8>, sp));
-    else GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_fast_kernel<16>, sp));
+    StreamParams fp = sp;
+    long long rf = (R + B - 1) / B;   // ranges per frame
+    if (rf > sp.batches_per_frame) rf = sp.batches_per_frame;
+    fp.rf = (int)rf;
+    fp.R = (int)rf * B;
+    fp.tb_base = (int)(sp.batches_per_frame / rf);
+    fp.tb_rem = (int)(sp.batches_per_frame % rf);
+    cfg.gridDim = dim3(fp.R * occ);
+    const bool full = (num_points & 31) == 0;
+    if (sp.row_words == 8) {
+      if (full) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<8, true>, fp));
+      else GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<8, false>, fp));
+    } else {
+      if (full) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<16, true>, fp));
+      else GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<16, false>, fp));
+    }
     return GGA_OK;
   }
   {

@@ -203,7 +203,8 @@ def test_points_in_boxes_cpu_signature_host_tensors():
 
 
 @pytest.mark.parametrize('T,frames,M', [(200, 3, 4000), (256, 5, 4096), (400, 3, 2048), (512, 2, 4128),
-                                        (700, 3, 2080), (1024, 2, 3200), (1024, 3, 999)])
+                                        (700, 3, 2080), (1024, 2, 3200), (1024, 3, 999), (256, 3, 4001), (400, 2, 1000),
+                                        (130, 4, 33), (512, 9, 31)])
 def test_multi_frame_bits_lean_widths(T, frames, M):
     """[F, N, 4] points, every row width of the lean stream variants (8/16/24/32 words), frames
     with different boxes in one call."""
