@@ -410,7 +410,7 @@ def run_ours(args):
             'metric': METRIC, 'value': round(value, 1), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': max(args.warmup, 3), 'ms_per_step': round(ms_per_step, 5), 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-            'roofline': {'bound': 'hbm', 'kernel': 'pib_prep_kernel + pib_stream_fast_kernel (membership, bit-packed; one C call, PDL-chained)', 'achieved': round(achieved, 1),
+            'roofline': {'bound': 'hbm', 'kernel': 'pib_prep_kernel + pib_stream_frame_kernel (membership, bit-packed; one C call, PDL-chained)', 'achieved': round(achieved, 1),
                          'peak': peak, 'unit': 'GB/s', 'frac': round(achieved / peak, 4), 'traffic': traffic,
                          'peak_source': peak_src, 'kernel_ms': round(kernel_ms, 5),
                          'algorithmic_bytes_per_launch': member_bytes,
