@@ -872,12 +872,13 @@ __global__ void __launch_bounds__(NT, GSM ? 1 : kOcc) pib_stream_kernel(const St
 // so instructions are what is being saved.
 // ------------------------------------------------------------------------------------------
 // Frame-local ranges: every range lies inside one frame (R = rf ranges per frame x frames), so a
-// CTA serves exactly one frame — its contract terms are always the shared-memory copy (LDS, no
-// generic-pointer select per candidate), the frame header and grid pointer are loop invariant and
-// the frame-crossing bookkeeping of the loop disappears.
+// CTA serves exactly one frame: one base pointer for its contract terms (no per-candidate select),
+// the frame header and grid pointer are loop invariant and the frame-crossing bookkeeping of the
+// loop disappears.  SP: the frame's terms are copied to shared memory first (candidate-heavy
+// scenes); otherwise they are read from global memory through L1 (sparse scenes, 40 registers).
 // FULL: N is a multiple of 32 (every batch has 32 points); otherwise the last batch of a frame is
 // ragged: its loads are clamped to the frame's last point and its surplus rows are not stored.
-template <int W, bool FULL>
+template <int W, bool FULL, bool SP>
 __global__ void __launch_bounds__(256, kOcc) pib_stream_frame_kernel(const StreamParams p) {
   constexpr int kW = 8;      // warps per CTA
   constexpr int kC = W / 4;  // 16-byte chunks of a row = store instructions per lane and batch
@@ -885,7 +886,7 @@ __global__ void __launch_bounds__(256, kOcc) pib_stream_frame_kernel(const Strea
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int stride = p.slots, T = p.num_boxes, N = p.num_points;
   const float4* prep_smem = reinterpret_cast<const float4*>(smem_all);
-  uint32_t* stage = smem_all + 8 * T + warp * (32 * W);
+  uint32_t* stage = smem_all + (SP ? 8 * T : 0) + warp * (32 * W);
 
   const int r = blockIdx.x % p.R, cta = (int)(blockIdx.x / p.R);
   const int f = r / p.rf, rr = r - f * p.rf;
@@ -900,12 +901,12 @@ __global__ void __launch_bounds__(256, kOcc) pib_stream_frame_kernel(const Strea
   if (g + stride < gend) v1 = load_pt(g + stride);
 
   asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the prep kernel wrote
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f * 2 * T;
+  const float4* prep_glob = reinterpret_cast<const float4*>(p.ws + p.L.prep) + (size_t)f * 2 * T;
+  if constexpr (SP) {
     float4* dst = reinterpret_cast<float4*>(smem_all);
-    for (int k = threadIdx.x; k < 2 * T; k += 256) dst[k] = ld_f4(src + k);
+    for (int k = threadIdx.x; k < 2 * T; k += 256) dst[k] = ld_f4(prep_glob + k);
+    __syncthreads();
   }
-  __syncthreads();
   if (g >= gend) return;
 
   const FrameCtx fc = load_frame(p, f);
@@ -922,7 +923,7 @@ __global__ void __launch_bounds__(256, kOcc) pib_stream_frame_kernel(const Strea
 #pragma unroll
     for (int k = 0; k < kC; ++k) reinterpret_cast<uint4*>(stage)[k * 32 + lane] = make_uint4(0, 0, 0, 0);
     __syncwarp();
-    for_each_hit(w, p, f, prep_smem, v.x, v.y, v.z,
+    for_each_hit(w, p, f, SP ? prep_smem : prep_glob, v.x, v.y, v.z,
                  [&](uint32_t t) { stage[lane * W + (t >> 5)] |= 1u << (t & 31u); });
     __syncwarp();
     uint4* dst = rows + (size_t)g * (32 * kC) + lane;
@@ -1082,37 +1083,45 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   }
   if (g_tune_phase == 1) return GGA_OK;
 
-  // lean variant: full 32-point batches, 8 / 16 row words, the frame's contract terms in shared memory
-  // (measured on B200: wider rows, whose terms stay in global memory, run faster in the generic kernel)
+  // lean variant: 8 / 16 row words, 16-byte points (wider rows run faster in the generic kernel)
   if (mode == kModeBits && sp.vec4 && (sp.row_words == 8 || sp.row_words == 16) && sp.smem_prep &&
       !g_tune_nofast && kStreamThreads == 256) {
-    const size_t fsmem = (size_t)num_boxes * 32 + (size_t)sp.row_words * 32 * 4 * 8;
+    // W = 8 (<= 256 boxes, sparse candidates): contract terms straight from global memory through
+    // L1 — a CTA touches a few dozen boxes, copying all of them to shared memory per CTA costs more
+    // than it saves (measured: 19.7 -> 18.4 us at c2), and the kernel then fits 40 registers.
+    // W = 16 (<= 512 boxes, candidate-heavy scenes): shared-memory copy (c3: 59.5 vs 65.6 us).
+    // (6 CTAs per SM with the 40-register variant: no gain.)
+    const bool use_sp = sp.row_words == 16;
+    const int occ_l = kOcc;
+    StreamParams fp = sp;
+    fp.slots = occ_l * 8;
+    long long Rl = (tb + fp.slots - 1) / fp.slots;
+    if (Rl > (long long)nsm * range_mult) Rl = (long long)nsm * range_mult;
+    long long rf = (Rl + B - 1) / B;   // ranges per frame
+    if (rf > sp.batches_per_frame) rf = sp.batches_per_frame;
+    if (rf < 1) rf = 1;
+    fp.rf = (int)rf;
+    fp.R = (int)rf * B;
+    fp.tb_base = (int)(sp.batches_per_frame / rf);
+    fp.tb_rem = (int)(sp.batches_per_frame % rf);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(fp.R * occ_l);
     cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = fsmem;
+    cfg.dynamicSmemBytes = (use_sp ? (size_t)num_boxes * 32 : 0) + (size_t)sp.row_words * 32 * 4 * 8;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    StreamParams fp = sp;
-    long long rf = (R + B - 1) / B;   // ranges per frame
-    if (rf > sp.batches_per_frame) rf = sp.batches_per_frame;
-    fp.rf = (int)rf;
-    fp.R = (int)rf * B;
-    fp.tb_base = (int)(sp.batches_per_frame / rf);
-    fp.tb_rem = (int)(sp.batches_per_frame % rf);
-    cfg.gridDim = dim3(fp.R * occ);
     const bool full = (num_points & 31) == 0;
+#define GGA_LEAN(W_, FULL_, SP_) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<W_, FULL_, SP_>, fp))
     if (sp.row_words == 8) {
-      if (full) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<8, true>, fp));
-      else GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<8, false>, fp));
+      if (full) GGA_LEAN(8, true, false); else GGA_LEAN(8, false, false);
     } else {
-      if (full) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<16, true>, fp));
-      else GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<16, false>, fp));
+      if (full) GGA_LEAN(16, true, true); else GGA_LEAN(16, false, true);
     }
+#undef GGA_LEAN
     return GGA_OK;
   }
   {
