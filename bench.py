@@ -395,7 +395,27 @@ def run_ours(args):
         ems = float(t.item())
     h2d, d2h = es.host_bytes(*eargs[:5])
     e2e = {'value': round(world * F * ereps / (ems * 1e-3), 1), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-           'd2h_bytes_per_step': int(d2h), 'steps': ereps, 'ms_per_step': round(ems / ereps, 4)}
+           'd2h_bytes_per_step': int(d2h), 'steps': ereps, 'ms_per_step': round(ems / ereps, 4),
+           'returns': 'masks + loss + box gradients to host memory (the points_in_boxes_cpu-style contract)'}
+    # same call with the masks left on the device (the training use: only loss and gradients go back)
+    for _ in range(3):
+        es.run_host(*eargs, n_streams=args.e2e_streams, masks_to_host=False)
+    barrier()
+    y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    y0.record()
+    for _ in range(ereps):
+        es.run_host(*eargs, n_streams=args.e2e_streams, masks_to_host=False)
+    y1.record()
+    barrier()
+    yms = y0.elapsed_time(y1)
+    if world > 1:
+        t = torch.tensor([yms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        yms = float(t.item())
+    e2e['masks_on_device'] = {'value': round(world * F * ereps / (yms * 1e-3), 1), 'unit': UNIT,
+                              'h2d_bytes_per_step': int(h2d),
+                              'd2h_bytes_per_step': int(es.host_bytes(*eargs[:5], masks_to_host=False)[1]),
+                              'ms_per_step': round(yms / ereps, 4)}
 
     # the same membership through the mmcv-layout entry point (int32 [F, N, M], what a drop-in
     # `points_in_boxes_all` caller gets): 21x the output bytes of the bit-packed rows, reported

@@ -108,7 +108,7 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
                                  uint32_t* bits, float* loss_sum, float* grad_boxes) {
   StepCtx* c = static_cast<StepCtx*>(ctx);
   GGA_REQUIRE(c != nullptr, "null context");
-  GGA_REQUIRE(points && boxes && lidar2img && target && bits && loss_sum && grad_boxes, "null host pointer");
+  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes, "null host pointer");
   GGA_REQUIRE(avg_factor > 0.f, "avg_factor must be positive");
   const size_t F = c->F, N = c->N, M = c->M, st = c->pts_stride, W = c->W;
   int dev = 0;
@@ -128,8 +128,9 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
     const int rc = gga_points_in_boxes_bits(c->d_points + f * N * st, (int)st, c->d_boxes + f * M * 7,
                                             c->d_bits + f * N * W, 1, (int)N, (int)M, c->d_ws[s], c->ws_bytes, q);
     if (rc != GGA_OK) return rc;
-    GGA_CHECK_CUDA(cudaMemcpyAsync(bits + f * N * W, c->d_bits + f * N * W, N * W * sizeof(uint32_t),
-                                   cudaMemcpyDeviceToHost, q));
+    if (bits)
+      GGA_CHECK_CUDA(cudaMemcpyAsync(bits + f * N * W, c->d_bits + f * N * W, N * W * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, q));
   }
   // projection + loss forward / backward
   cudaStream_t b = c->box_stream;
@@ -154,5 +155,12 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
     gga_set_error("gga_step_run_host: %s", cudaGetErrorString(e));
     return GGA_ERR_CUDA;
   }
+  return GGA_OK;
+}
+
+extern "C" int gga_step_device_bits(void* ctx, uint32_t** bits_device) {
+  StepCtx* c = static_cast<StepCtx*>(ctx);
+  GGA_REQUIRE(c != nullptr && bits_device != nullptr, "null argument");
+  *bits_device = c->d_bits;
   return GGA_OK;
 }

@@ -119,9 +119,12 @@ class GeometryStep:
             a.loss_accum = self.loss_accum.data_ptr()
         return a
 
-    def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3):
+    def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3, masks_to_host=True):
         """Same step with HOST inputs (page-locked torch CPU tensors) and HOST results: returns
         (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous.
+        ``masks_to_host=False`` leaves the masks on the device (the training use: the head consumes
+        them there) and returns a CUDA int32 tensor view of the library's buffer instead — valid
+        until the next ``run_host`` / ``close``.
 
         One C call (``gga_step_run_host``): the PCIe link is the bound (46 MB per step at the
         training shape), so the library pipelines the step frame by frame over `n_streams`
@@ -149,8 +152,24 @@ class GeometryStep:
                 h['ctx'], points.data_ptr(), boxes.data_ptr(), lidar2img.data_ptr(), target.data_ptr(),
                 None if weight is None else weight.data_ptr(), self.mode, self.kind, self.loss_weight,
                 float(avg_factor if avg_factor is not None else max(n, 1)), self.eps, self.depth_clamp,
-                h['h_bits'].data_ptr(), h['h_loss'].data_ptr(), h['h_grad'].data_ptr()), 'step_run_host')
+                h['h_bits'].data_ptr() if masks_to_host else None, h['h_loss'].data_ptr(), h['h_grad'].data_ptr()),
+                'step_run_host')
+        if not masks_to_host:
+            return self._device_bits(), float(h['h_loss'][0]), h['h_grad']
         return h['h_bits'], float(h['h_loss'][0]), h['h_grad']
+
+    def _device_bits(self):
+        h = self._host
+        if 'd_bits' not in h:
+            ptr = _lib.c_void_p()
+            _lib.check(self.L.gga_step_device_bits(h['ctx'], ctypes.byref(ptr)), 'step_device_bits')
+
+            class _Buf:   # zero-copy view of the library-owned device buffer
+                __cuda_array_interface__ = {'shape': tuple(self.bits.shape), 'typestr': '<i4', 'data': (ptr.value, False),
+                                            'version': 2}
+            h['d_bits_owner'] = _Buf()
+            h['d_bits'] = torch.as_tensor(h['d_bits_owner'], device=self.device)
+        return h['d_bits']
 
     def close(self):
         """Releases the device context of the host-buffer path (idempotent)."""
@@ -164,8 +183,8 @@ class GeometryStep:
         except Exception:
             pass
 
-    def host_bytes(self, points, boxes, lidar2img, target, weight):
+    def host_bytes(self, points, boxes, lidar2img, target, weight, masks_to_host=True):
         """(h2d, d2h) bytes moved by one ``run_host``."""
         h2d = sum(t.numel() * t.element_size() for t in (points, boxes, lidar2img, target, weight))
-        d2h = self.bits.numel() * 4 + self.grad_boxes.numel() * 4 + 4
+        d2h = (self.bits.numel() * 4 if masks_to_host else 0) + self.grad_boxes.numel() * 4 + 4
         return h2d, d2h

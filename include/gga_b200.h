@@ -328,6 +328,11 @@ int gga_step_run_host(void* ctx, const float* points, const float* boxes, const 
                       const float* target, const float* weight, int proj_mode, int loss_kind,
                       float loss_weight, float avg_factor, float eps, float depth_clamp,
                       uint32_t* bits, float* loss_sum, float* grad_boxes);
+/* `bits` may be NULL: the masks then stay on the device (the training use — the reference's GPU op
+ * `points_in_boxes_all` leaves them there too, base_box3d.py:566) and only loss and gradients come
+ * back.  gga_step_device_bits() gives the device buffer [F, N, W] they are in, valid until the
+ * next run or destroy. */
+int gga_step_device_bits(void* ctx, uint32_t** bits_device);
 
 /* ------------------------------------------------------------------------------------
  * Test hooks (device build of include/gga_detmath.h and of the per-box preparation).

@@ -68,6 +68,13 @@ def test_step_matches_oracle_eager_graph_and_host():
         _check(hs, bits, loss_sum, grad, ref)
     h2d, d2h = hs.host_bytes(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'])
     assert h2d == sum(v.nbytes for v in bt.values()) and d2h == F * N * step.W * 4 + F * M * 7 * 4 + 4
+    # training use: masks stay on the device, only loss and gradients come back
+    dbits, loss_sum, grad = hs.run_host(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'],
+                                        hin['weight'], float(F * M), masks_to_host=False)
+    assert dbits.is_cuda and dbits.dtype == torch.int32 and not grad.is_cuda
+    _check(hs, dbits.cpu(), loss_sum, grad, ref)
+    assert hs.host_bytes(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'],
+                         masks_to_host=False)[1] == F * M * 7 * 4 + 4
 
 
 def test_workspace_contract_unzeroed_and_shared_sizes():
