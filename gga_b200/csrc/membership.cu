@@ -864,7 +864,7 @@ __global__ void __launch_bounds__(NT, GSM ? 1 : kOcc) pib_stream_kernel(const St
 }
 
 // ------------------------------------------------------------------------------------------
-// stream kernel, lean variant for the training shapes: bit-packed rows of 8 / 16 words (129..512
+// stream kernel, lean variant for the training shapes: bit-packed rows of 8 .. 32 words (129..1024
 // boxes), 16-byte points.  Batch g of a frame is points[32 g .. 32 g + 31] and rows
 // out[32 g ..] (16-byte aligned because rows are multiples of 16 bytes), and the per-batch
 // bookkeeping of the general kernel (frame decode, alignment and tail paths: ~60 of its ~240
@@ -1083,13 +1083,14 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   }
   if (g_tune_phase == 1) return GGA_OK;
 
-  // lean variant: 8 / 16 row words, 16-byte points (wider rows run faster in the generic kernel)
-  if (mode == kModeBits && sp.vec4 && (sp.row_words == 8 || sp.row_words == 16) && sp.smem_prep &&
-      !g_tune_nofast && kStreamThreads == 256) {
+  // lean variant: bit-packed rows of 8 / 16 / 24 / 32 words (129..1024 boxes), 16-byte points
+  if (mode == kModeBits && sp.vec4 && !g_tune_nofast && kStreamThreads == 256 && (sp.row_words & 7) == 0 &&
+      sp.row_words <= 32) {
     // W = 8 (<= 256 boxes, sparse candidates): contract terms straight from global memory through
     // L1 — a CTA touches a few dozen boxes, copying all of them to shared memory per CTA costs more
     // than it saves (measured: 19.7 -> 18.4 us at c2), and the kernel then fits 40 registers.
     // W = 16 (<= 512 boxes, candidate-heavy scenes): shared-memory copy (c3: 59.5 vs 65.6 us).
+    // W = 24 / 32: global memory again (32 KB of terms per CTA would halve the occupancy); c5 82 -> 74 us.
     // (6 CTAs per SM with the 40-register variant: no gain.)
     const bool use_sp = sp.row_words == 16;
     const int occ_l = kOcc;
@@ -1118,6 +1119,10 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
 #define GGA_LEAN(W_, FULL_, SP_) GGA_CHECK_CUDA(cudaLaunchKernelEx(&cfg, pib_stream_frame_kernel<W_, FULL_, SP_>, fp))
     if (sp.row_words == 8) {
       if (full) GGA_LEAN(8, true, false); else GGA_LEAN(8, false, false);
+    } else if (sp.row_words == 24) {
+      if (full) GGA_LEAN(24, true, false); else GGA_LEAN(24, false, false);
+    } else if (sp.row_words == 32) {
+      if (full) GGA_LEAN(32, true, false); else GGA_LEAN(32, false, false);
     } else {
       if (full) GGA_LEAN(16, true, true); else GGA_LEAN(16, false, true);
     }
