@@ -9,7 +9,8 @@ from .project import box3d_project, pad_proj
 from .losses import (AxisAlignedIoULoss, GIoULoss, IoULoss, L1Loss, ProjectedGIoULoss, ProjectedIoULoss,
                      ProjectedL1Loss, axis_aligned_iou_loss, box2d_loss, projected_box_loss)
 from . import np_ops
-from .np_ops import face_distances, points_in_convex_polygon_3d_jit, points_in_frustm_indices, points_in_rbbox
+from .np_ops import (box3d_to_bbox, face_distances, iou_jit, points_in_convex_polygon_3d_jit, points_in_frustm_indices,
+                     points_in_rbbox)
 from .matching import convert_valid_bboxes_batch, image_box_overlap, match_dt_to_gt
 from .head import (boundary_projection_loss, get_distance_bev, get_prediction_single, gga_calculate_rotation,
                    pack_in_box_points, point_alignment_losses, point_box_distances)
@@ -25,6 +26,6 @@ __all__ = [
     'convert_valid_bboxes_batch', 'image_box_overlap', 'match_dt_to_gt', 'get_prediction_single',
     'gga_calculate_rotation', 'boundary_projection_loss', 'get_distance_bev', 'pack_in_box_points',
     'point_box_distances', 'point_alignment_losses', 'get_targets', 'pack_targets', 'semantic_ratio_samples',
-    'bbox2result_kitti', 'kitti_lines', 'pseudo_label_matching_kitti',
+    'bbox2result_kitti', 'kitti_lines', 'pseudo_label_matching_kitti', 'box3d_to_bbox', 'iou_jit',
 ]
 __version__ = '0.1.0'

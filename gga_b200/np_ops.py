@@ -177,3 +177,38 @@ def face_distances(points, boxes, return_inside=False):
         _lib.check(_lib.load().gga_face_distances(_lib.ptr(p), _lib.ptr(b), n, m, _lib.ptr(dist), _lib.ptr(inside),
                                                   _lib.current_stream(p.device)), 'face_distances')
     return (dist, inside.bool()) if return_inside else dist
+
+
+def box3d_to_bbox(box3d, P2, device='cuda'):
+    """``box_np_ops.box3d_to_bbox`` (box_np_ops.py:311-328): camera boxes [N, 7] numpy and P2 ->
+    [N, 4] = (min xy, max xy) of the 8 projected corners; corners with origin (0.5, 1.0, 0.5),
+    rotation about y (:171-200), ``points_cam2img`` (structures/utils.py:175-214).  One
+    ``box3d_project(mode='cam_bottom')`` launch; float32 arithmetic like the reference's
+    array_converter path, result in the input dtype."""
+    from .project import box3d_project
+    b = np.asarray(box3d)
+    if b.shape[0] == 0:
+        return np.zeros((0, 4), dtype=b.dtype)
+    dev = torch.device(device)
+    tb = torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(dev)
+    tp = torch.from_numpy(np.ascontiguousarray(P2, dtype=np.float32)).to(dev)
+    out, _ = box3d_project(tb, tp, mode='cam_bottom')
+    return out.cpu().numpy().astype(b.dtype)
+
+
+def iou_jit(boxes, query_boxes, mode='iou', eps=0.0, device='cuda'):
+    """``box_np_ops.iou_jit`` (box_np_ops.py:482-523): pairwise 2D IoU [N, K] of numpy boxes with
+    ``eps`` added to every width / height / intersection side; ``mode != 'iou'`` divides by the
+    area of ``boxes[n]`` only.  Adding eps to (x2, y2) of both sets turns this into the eps-free
+    ``image_box_overlap`` kernel (criterion -1 / 0), evaluated in float64 and cast to
+    ``boxes.dtype`` (the reference's numba loop mixes float32 differences with the float64 eps)."""
+    from .matching import image_box_overlap
+    b, q = np.asarray(boxes), np.asarray(query_boxes)
+    if b.shape[0] == 0 or q.shape[0] == 0:
+        return np.zeros((b.shape[0], q.shape[0]), dtype=b.dtype)
+    dev = torch.device(device)
+    grow = np.array([0.0, 0.0, eps, eps])
+    tb = torch.from_numpy(b[:, :4].astype(np.float64) + grow).to(dev)
+    tq = torch.from_numpy(q[:, :4].astype(np.float64) + grow).to(dev)
+    ov = image_box_overlap(tb, tq, criterion=-1 if mode == 'iou' else 0)
+    return ov.cpu().numpy().astype(b.dtype)

@@ -361,6 +361,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, 'ref_convex.npz'), **cp)
     gen_targets()
     gen_format()
+    gen_npops()
     print('wrote', sorted(os.listdir(OUT)))
 
 
@@ -451,8 +452,37 @@ def gen_format():
     np.savez_compressed(os.path.join(OUT, 'ref_format.npz'), **g)
 
 
+def gen_npops():
+    """tests/golden/ref_npops.npz: the reference's own box_np_ops.box3d_to_bbox (:311-328) and
+    iou_jit (:482-523) on camera boxes / 2D boxes (rows a16 and a25 of SURVEY.md §8a)."""
+    ref = ref_loader.load_reference()
+    rng = np.random.default_rng(1625)
+    n = 96
+    cam = np.concatenate([rng.uniform(-15, 15, (n, 1)), rng.uniform(0.5, 2.5, (n, 1)), rng.uniform(4, 60, (n, 1)),
+                          rng.uniform(0.5, 4.5, (n, 3)), rng.uniform(-np.pi, np.pi, (n, 1))], 1)
+    g = {}
+    for name, dt in (('f32', np.float32), ('f64', np.float64)):
+        b = cam.astype(dt)
+        g[f'cam_{name}'] = b
+        g[f'bbox_{name}'] = ref.box_np_ops.box3d_to_bbox(b, P2.astype(dt))
+    g['P2'] = P2
+    x1y1 = np.stack([rng.uniform(0, 1100, 70), rng.uniform(0, 300, 70)], 1)
+    bx = np.concatenate([x1y1, x1y1 + rng.uniform(1, 250, (70, 2))], 1)
+    bx[5] = bx[6]                       # identical boxes
+    bx[7, 2:] = bx[7, :2]               # zero-area box
+    q = bx[::2] + rng.normal(0, 8, (35, 4))
+    for name, dt in (('f32', np.float32), ('f64', np.float64)):
+        g[f'iou_boxes_{name}'], g[f'iou_query_{name}'] = bx.astype(dt), q.astype(dt)
+        for mode in ('iou', 'iof'):
+            for eps in (0.0, 1.0):
+                g[f'iou_{name}_{mode}_{int(eps)}'] = ref.box_np_ops.iou_jit(bx.astype(dt), q.astype(dt), mode, eps)
+    np.savez_compressed(os.path.join(OUT, 'ref_npops.npz'), **g)
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] == ['targets']:
+    if sys.argv[1:] == ['npops']:
+        gen_npops()
+    elif sys.argv[1:] == ['targets']:
         gen_targets()
     elif sys.argv[1:] == ['format']:
         gen_format()
