@@ -472,7 +472,13 @@ def run_ours(args):
                          'peak_source': peak_src, 'kernel_ms': round(kernel_ms, 5),
                          'algorithmic_bytes_per_launch': member_bytes,
                          'step_frac_of_hbm_roofline': round(all_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
-                         'mmcv_layout': mmcv_layout},
+                         'mmcv_layout': mmcv_layout,
+                         # the brute-force definition of the work (14 FP32 instructions per
+                         # point-box pair) over the same launch time; > 1 x the 74.4 TFLOP/s FP32 peak is what
+                         # the conservative culling buys (ncu: the FMA pipe is ~17 % busy)
+                         'fp32_bruteforce_equivalent': {'flops_per_launch': 14 * F * N * M,
+                                                        'tflops': round(14 * F * N * M / (kernel_ms * 1e-3) / 1e12, 1),
+                                                        'peak_tflops': 74.4}},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': 3 * args.steps,
             'clocks': sampler.summary(),
         }
