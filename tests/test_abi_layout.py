@@ -45,3 +45,37 @@ def test_struct_layout_matches_the_header(tmp_path, cname, mirror):
     assert vals[0] == ctypes.sizeof(mirror)
     for n, off in zip(names, vals[1:]):
         assert getattr(mirror, n).offset == off, n
+
+
+def test_a_plain_c_program_can_load_and_call_the_library(tmp_path):
+    """dlopen from C (no Python, no torch in the process): the entry points that need no device."""
+    lib = _lib.library_path() if hasattr(_lib, 'library_path') else os.path.join(ROOT, 'gga_b200', '_C', 'libgga_b200.so')
+    if not os.path.isfile(lib):
+        from gga_b200 import build
+        build.build(verbose=False)
+    prog = r'''
+#include <dlfcn.h>
+#include <stdio.h>
+#include "%s"
+int main(int argc, char** argv) {
+  void* h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);
+  if (!h) { fprintf(stderr, "%%s\n", dlerror()); return 2; }
+  int (*version)(void) = (int (*)(void))dlsym(h, "gga_version");
+  int (*row_words)(int) = (int (*)(int))dlsym(h, "gga_pib_row_words");
+  size_t (*ws_bytes)(int, int, int) = (size_t (*)(int, int, int))dlsym(h, "gga_pib_workspace_bytes");
+  int (*bits)(const float*, int, const float*, uint32_t*, int, int, int, void*, size_t, void*) =
+      (int (*)(const float*, int, const float*, uint32_t*, int, int, int, void*, size_t, void*))dlsym(h, "gga_points_in_boxes_bits");
+  const char* (*last_error)(void) = (const char* (*)(void))dlsym(h, "gga_last_error");
+  if (!version || !row_words || !ws_bytes || !bits || !last_error) return 3;
+  int rc = bits(NULL, 2, NULL, NULL, 1, 8, 8, NULL, 0, NULL);   /* pts_stride < 3: rejected before any CUDA call */
+  printf("%%d %%d %%d %%zu %%d %%s\n", version(), row_words(256), row_words(1024), ws_bytes(8, 120000, 256), rc, last_error());
+  return 0;
+}
+''' % HEADER
+    src = tmp_path / 'use.c'
+    src.write_text(prog)
+    exe = tmp_path / 'use'
+    subprocess.run(['/usr/bin/gcc', '-std=c11', '-Wall', '-o', str(exe), str(src), '-ldl'], check=True)
+    out = subprocess.run([str(exe), lib], check=True, capture_output=True, text=True).stdout.split(None, 5)
+    assert int(out[0]) >= 100 and int(out[1]) == 8 and int(out[2]) == 32 and int(out[3]) > 0
+    assert int(out[4]) == -1 and 'pts_stride' in out[5]
