@@ -344,8 +344,7 @@ def run_ours(args):
     def member(i):
         t, s = sets[i % n_sets], steps[i % n_sets]
         st = torch.cuda.current_stream().cuda_stream
-        rc = L.gga_points_in_boxes_bits(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), s.bits.data_ptr(), F, N, M,
-                                        s.ws.data_ptr(), s.ws.numel(), st)
+        rc = L.gga_points_in_boxes_bits(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), s.bits.data_ptr(), F, N, M, st)
         assert rc == 0
     for i in range(n_sets):
         member(i)
@@ -427,8 +426,7 @@ def run_ours(args):
         def member_all(i):
             t, s = sets[i % n_sets], steps[i % n_sets]
             rc = L.gga_points_in_boxes_all(t['points'].data_ptr(), 4, t['boxes'].data_ptr(), a_outs[i % 2].data_ptr(),
-                                           F, N, M, s.ws.data_ptr(), s.ws.numel(),
-                                           torch.cuda.current_stream().cuda_stream)
+                                           F, N, M, torch.cuda.current_stream().cuda_stream)
             assert rc == 0
         for i in range(2):
             member_all(i)

@@ -29,6 +29,7 @@ class BoxLossArgs(ctypes.Structure):
         ('box2d', c_void_p), ('valid', c_void_p), ('argidx', c_void_p), ('loss', c_void_p),
         ('loss_sum', c_void_p), ('loss_accum', c_void_p), ('grad_boxes', c_void_p), ('grad_box2d', c_void_p),
         ('grad_target', c_void_p),
+        ('scratch', c_void_p), ('scratch_bytes', ctypes.c_size_t),
     ]
 
 
@@ -58,23 +59,19 @@ SIGNATURES = {
     'gga_last_error': ([], ctypes.c_char_p),
     'gga_device_info': ([ctypes.POINTER(c_int)] * 3 + [ctypes.POINTER(ctypes.c_size_t)], c_int),
     'gga_pib_row_words': ([c_int], c_int),
-    'gga_pib_workspace_bytes': ([c_int, c_int, c_int], ctypes.c_size_t),
-    'gga_pib_workspace_init': ([c_void_p, ctypes.c_size_t, c_void_p], c_int),
-    'gga_points_in_boxes_bits': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                  ctypes.c_size_t, c_void_p], c_int),
-    'gga_points_in_boxes_all': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                 ctypes.c_size_t, c_void_p], c_int),
-    'gga_points_in_boxes_part': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                  ctypes.c_size_t, c_void_p], c_int),
+    'gga_points_in_boxes_bits': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    'gga_points_in_boxes_all': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
+    'gga_points_in_boxes_part': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     'gga_points_in_boxes_all_host': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int], c_int),
-    'gga_pib_set_tuning': ([c_int, c_int], c_int),
     'gga_box_project_loss': ([ctypes.POINTER(BoxLossArgs), c_void_p], c_int),
     'gga_box_project_backward': ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, ctypes.c_float, c_void_p], c_int),
+    'gga_loss_scratch_bytes': ([], ctypes.c_size_t),
     'gga_box2d_loss': ([c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, ctypes.c_float,
-                        ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+                        ctypes.c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_size_t,
+                        c_void_p], c_int),
     'gga_box3d_aa_loss': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, ctypes.c_float, ctypes.c_float,
-                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p], c_int),
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_size_t, c_void_p], c_int),
     'gga_match_dt_gt': ([c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p], c_int),
     'gga_image_box_overlap_f64': ([c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p], c_int),
@@ -91,11 +88,13 @@ SIGNATURES = {
     'gga_step_run_host': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                            ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                            c_void_p, c_void_p, c_void_p], c_int),
-    'gga_test_pib_phase': ([c_int], c_int),
-    'gga_test_pib_trace': ([c_void_p], c_int),
-    'gga_test_pib_trace_prep': ([c_void_p], c_int),
     'gga_test_sincos': ([c_void_p, ctypes.c_int64, c_void_p, c_void_p, c_void_p], c_int),
     'gga_test_box_prep': ([c_void_p, c_int, c_void_p, c_void_p], c_int),
+}
+
+# developer hooks of GGA_PROFILING builds (tools/build_prof.py); absent from the product library
+DEV_SIGNATURES = {
+    'gga_prof_pib': ([c_int, c_int, c_int, c_void_p], c_int),
 }
 
 PROJ_LIDAR_DIRECT, PROJ_KITTI_CAM, PROJ_CAM_CENTER, PROJ_CAM_BOTTOM = 0, 1, 2, 3
@@ -119,11 +118,14 @@ def load():
             _build.build()
         L = ctypes.CDLL(_LIB_PATH)
         for name, (argtypes, restype) in SIGNATURES.items():
-            if name.startswith('gga_test_') and not hasattr(L, name):
-                continue  # profiling / test hooks are optional (A/B runs against older builds)
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.argtypes = argtypes
             fn.restype = restype
+        for name, (argtypes, restype) in DEV_SIGNATURES.items():
+            if hasattr(L, name):
+                fn = getattr(L, name)
+                fn.argtypes = argtypes
+                fn.restype = restype
         _lib = L
     return _lib
 
@@ -132,6 +134,27 @@ def check(rc, what=''):
     if rc != 0:
         msg = load().gga_last_error().decode('utf-8', 'replace')
         raise RuntimeError(f'libgga_b200 {what} failed (code {rc}): {msg}')
+
+
+_SCRATCH = {}
+
+
+def loss_scratch(device):
+    """Zeroed scratch tensor for one loss-reduction call on the CURRENT stream of `device`
+    (include/gga_b200.h: caller-owned, zeroed once, not shared by concurrent calls).  Cached per
+    (device, stream): calls on one stream are ordered and the kernels leave it zeroed.  Under
+    CUDA-graph capture a private tensor is returned (the graph keeps it alive)."""
+    import torch
+    device = torch.device(device)
+    nbytes = int(load().gga_loss_scratch_bytes())
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    s = _SCRATCH.get(key)
+    if s is None:
+        s = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
+        _SCRATCH[key] = s
+    return s
 
 
 def ptr(t):

@@ -22,28 +22,25 @@
 namespace {
 
 constexpr int kBoxThreads = 128;
-constexpr int kSlots = 64;
 constexpr int kMaxPartials = 1024;
 
-struct Workspace {
-  unsigned int counter[kSlots];
-  float partial[kSlots][kMaxPartials];
+// Caller-owned scratch of the deterministic loss reduction (include/gga_b200.h,
+// gga_loss_scratch_bytes): an arrival counter the kernel leaves at zero, and the per-block
+// partial sums the last block adds in index order.  Nothing is shared between calls.
+struct LossScratch {
+  unsigned int counter;
+  unsigned int pad[3];
+  float partial[kMaxPartials];
 };
 
-Workspace* g_ws[64];
-unsigned int g_slot = 0;
-
-int get_workspace(Workspace** ws) {
-  int dev = 0;
-  GGA_CHECK_CUDA(cudaGetDevice(&dev));
-  GGA_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
-  if (!g_ws[dev]) {
-    Workspace* w = nullptr;
-    GGA_CHECK_CUDA(cudaMalloc(&w, sizeof(Workspace)));
-    GGA_CHECK_CUDA(cudaMemset(w, 0, sizeof(Workspace)));
-    g_ws[dev] = w;
-  }
-  *ws = g_ws[dev];
+int scratch_of(void* scratch, size_t scratch_bytes, float** partial, unsigned int** counter) {
+  GGA_REQUIRE(scratch != nullptr, "loss_sum needs scratch (gga_loss_scratch_bytes() bytes, zeroed once)");
+  GGA_REQUIRE(scratch_bytes >= sizeof(LossScratch), "scratch too small: %zu bytes given, %zu needed", scratch_bytes,
+              sizeof(LossScratch));
+  GGA_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15u) == 0, "scratch must be 16-byte aligned");
+  LossScratch* s = static_cast<LossScratch*>(scratch);
+  *partial = s->partial;
+  *counter = &s->counter;
   return GGA_OK;
 }
 
@@ -611,6 +608,8 @@ int blocks_for(int n) {
 
 }  // namespace
 
+extern "C" size_t gga_loss_scratch_bytes(void) { return sizeof(LossScratch); }
+
 extern "C" int gga_box_project_loss(const gga_box_loss_args* args, void* stream) {
   GGA_REQUIRE(args != nullptr, "null args");
   const gga_box_loss_args& a = *args;
@@ -637,12 +636,8 @@ extern "C" int gga_box_project_loss(const gga_box_loss_args* args, void* stream)
   A.partial = nullptr;
   A.counter = nullptr;
   if (a.loss_sum) {
-    Workspace* ws;
-    const int rc = get_workspace(&ws);
+    const int rc = scratch_of(a.scratch, a.scratch_bytes, &A.partial, &A.counter);
     if (rc != GGA_OK) return rc;
-    const unsigned int slot = (g_slot++) % kSlots;
-    A.partial = ws->partial[slot];
-    A.counter = &ws->counter[slot];
   }
   box_loss_kernel<<<blocks_for(a.n), kBoxThreads, 0, st>>>(A);
   GGA_CHECK_CUDA(cudaGetLastError());
@@ -669,7 +664,7 @@ extern "C" int gga_box_project_backward(const float* boxes, const float* proj, i
 extern "C" int gga_box2d_loss(const float* pred, const float* target, const float* weight,
                               int weight_cols, const float* grad_loss, int n, int loss_kind, float eps,
                               float grad_scale, float* loss, float* loss_sum, float* grad_pred,
-                              float* grad_target, void* stream) {
+                              float* grad_target, void* scratch, size_t scratch_bytes, void* stream) {
   GGA_REQUIRE(n >= 0, "negative n");
   GGA_REQUIRE(loss_kind >= GGA_LOSS_GIOU && loss_kind <= GGA_LOSS_L1, "bad loss kind %d", loss_kind);
   cudaStream_t st = gga_stream(stream);
@@ -682,12 +677,8 @@ extern "C" int gga_box2d_loss(const float* pred, const float* target, const floa
   float* partial = nullptr;
   unsigned int* counter = nullptr;
   if (loss_sum) {
-    Workspace* ws;
-    const int rc = get_workspace(&ws);
+    const int rc = scratch_of(scratch, scratch_bytes, &partial, &counter);
     if (rc != GGA_OK) return rc;
-    const unsigned int slot = (g_slot++) % kSlots;
-    partial = ws->partial[slot];
-    counter = &ws->counter[slot];
   }
   box2d_loss_kernel<<<blocks_for(n), kBoxThreads, 0, st>>>(pred, target, weight, weight_cols, grad_loss,
                                                            n, loss_kind, eps, grad_scale, loss,
@@ -700,7 +691,7 @@ extern "C" int gga_box2d_loss(const float* pred, const float* target, const floa
 extern "C" int gga_box3d_aa_loss(const float* pred, const float* target, const float* weight,
                                  const float* grad_loss, int n, int giou, float eps, float grad_scale,
                                  float* loss, float* loss_sum, float* grad_pred, float* grad_target,
-                                 void* stream) {
+                                 void* scratch, size_t scratch_bytes, void* stream) {
   GGA_REQUIRE(n >= 0, "negative n");
   cudaStream_t st = gga_stream(stream);
   if (n == 0) {
@@ -712,12 +703,8 @@ extern "C" int gga_box3d_aa_loss(const float* pred, const float* target, const f
   float* partial = nullptr;
   unsigned int* counter = nullptr;
   if (loss_sum) {
-    Workspace* ws;
-    const int rc = get_workspace(&ws);
+    const int rc = scratch_of(scratch, scratch_bytes, &partial, &counter);
     if (rc != GGA_OK) return rc;
-    const unsigned int slot = (g_slot++) % kSlots;
-    partial = ws->partial[slot];
-    counter = &ws->counter[slot];
   }
   box3d_aa_loss_kernel<<<blocks_for(n), kBoxThreads, 0, st>>>(pred, target, weight, grad_loss, n, giou, eps,
                                                               grad_scale, loss, loss_sum, grad_pred,

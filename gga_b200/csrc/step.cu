@@ -30,8 +30,8 @@ struct StepCtx {
   float* d_loss;      // [F*M]
   float* d_loss_sum;  // [1]
   float* d_grad;      // [F*M, 7]
-  void* d_ws[kMaxStreams];
-  size_t ws_bytes;
+  void* d_scratch;    // loss-reduction scratch of this context (zeroed at creation)
+  size_t scratch_bytes;
   cudaStream_t streams[kMaxStreams];
   cudaStream_t box_stream;
   cudaEvent_t boxes_ready, done[kMaxStreams], box_done;
@@ -41,8 +41,8 @@ void destroy(StepCtx* c) {
   if (!c) return;
   cudaFree(c->d_points); cudaFree(c->d_boxes); cudaFree(c->d_proj); cudaFree(c->d_target); cudaFree(c->d_weight);
   cudaFree(c->d_bits); cudaFree(c->d_box2d); cudaFree(c->d_loss); cudaFree(c->d_loss_sum); cudaFree(c->d_grad);
+  cudaFree(c->d_scratch);
   for (int i = 0; i < kMaxStreams; ++i) {
-    if (c->d_ws[i]) cudaFree(c->d_ws[i]);
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->done[i]) cudaEventDestroy(c->done[i]);
   }
@@ -79,10 +79,11 @@ extern "C" int gga_step_create(int num_frames, int num_points, int num_boxes, in
   if (e == cudaSuccess) e = cudaMalloc(&c->d_loss, F * M * 4 * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_loss_sum, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_grad, F * M * 7 * sizeof(float));
-  c->ws_bytes = gga_pib_workspace_bytes(1, num_points, num_boxes);
+  c->scratch_bytes = gga_loss_scratch_bytes();
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_scratch, c->scratch_bytes);
+  if (e == cudaSuccess) e = cudaMemset(c->d_scratch, 0, c->scratch_bytes);
   for (int i = 0; i < n_streams && e == cudaSuccess; ++i) {
-    e = cudaMalloc(&c->d_ws[i], c->ws_bytes);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->box_stream, cudaStreamNonBlocking);
@@ -102,19 +103,12 @@ extern "C" int gga_step_destroy(void* ctx) {
   return GGA_OK;
 }
 
-extern "C" int gga_step_run_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
-                                 const float* target, const float* weight, int proj_mode, int loss_kind,
-                                 float loss_weight, float avg_factor, float eps, float depth_clamp,
-                                 uint32_t* bits, float* loss_sum, float* grad_boxes) {
-  StepCtx* c = static_cast<StepCtx*>(ctx);
-  GGA_REQUIRE(c != nullptr, "null context");
-  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes, "null host pointer");
-  GGA_REQUIRE(avg_factor > 0.f, "avg_factor must be positive");
+// Enqueues the whole step; returns on the first failure WITHOUT synchronising (the caller does).
+static int enqueue_step(StepCtx* c, const float* points, const float* boxes, const float* lidar2img,
+                        const float* target, const float* weight, int proj_mode, int loss_kind, float loss_weight,
+                        float avg_factor, float eps, float depth_clamp, uint32_t* bits, float* loss_sum,
+                        float* grad_boxes) {
   const size_t F = c->F, N = c->N, M = c->M, st = c->pts_stride, W = c->W;
-  int dev = 0;
-  GGA_CHECK_CUDA(cudaGetDevice(&dev));
-  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
-
   // boxes first: every frame's membership needs them
   GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_boxes, boxes, F * M * 7 * sizeof(float), cudaMemcpyHostToDevice, c->box_stream));
   GGA_CHECK_CUDA(cudaEventRecord(c->boxes_ready, c->box_stream));
@@ -126,7 +120,7 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
     GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_points + f * N * st, points + f * N * st, N * st * sizeof(float),
                                    cudaMemcpyHostToDevice, q));
     const int rc = gga_points_in_boxes_bits(c->d_points + f * N * st, (int)st, c->d_boxes + f * M * 7,
-                                            c->d_bits + f * N * W, 1, (int)N, (int)M, c->d_ws[s], c->ws_bytes, q);
+                                            c->d_bits + f * N * W, 1, (int)N, (int)M, q);
     if (rc != GGA_OK) return rc;
     if (bits)
       GGA_CHECK_CUDA(cudaMemcpyAsync(bits + f * N * W, c->d_bits + f * N * W, N * W * sizeof(uint32_t),
@@ -144,13 +138,35 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
   a.n = (int)(F * M); a.mode = proj_mode; a.loss_kind = loss_kind;
   a.depth_clamp = depth_clamp; a.eps = eps; a.grad_scale = loss_weight / avg_factor;
   a.box2d = c->d_box2d; a.loss = c->d_loss; a.loss_sum = c->d_loss_sum; a.grad_boxes = c->d_grad;
+  a.scratch = c->d_scratch; a.scratch_bytes = c->scratch_bytes;
   const int rc = gga_box_project_loss(&a, b);
   if (rc != GGA_OK) return rc;
   GGA_CHECK_CUDA(cudaMemcpyAsync(grad_boxes, c->d_grad, F * M * 7 * sizeof(float), cudaMemcpyDeviceToHost, b));
   GGA_CHECK_CUDA(cudaMemcpyAsync(loss_sum, c->d_loss_sum, sizeof(float), cudaMemcpyDeviceToHost, b));
-  // the call is synchronous, like the CPU op it stands in for
-  cudaError_t e = cudaStreamSynchronize(b);
-  for (int s = 0; s < c->n_streams && e == cudaSuccess; ++s) e = cudaStreamSynchronize(c->streams[s]);
+  return GGA_OK;
+}
+
+extern "C" int gga_step_run_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                                 const float* target, const float* weight, int proj_mode, int loss_kind,
+                                 float loss_weight, float avg_factor, float eps, float depth_clamp,
+                                 uint32_t* bits, float* loss_sum, float* grad_boxes) {
+  StepCtx* c = static_cast<StepCtx*>(ctx);
+  GGA_REQUIRE(c != nullptr, "null context");
+  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes, "null host pointer");
+  GGA_REQUIRE(avg_factor > 0.f, "avg_factor must be positive");
+  int dev = 0;
+  GGA_CHECK_CUDA(cudaGetDevice(&dev));
+  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
+  const int rc = enqueue_step(c, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight,
+                              avg_factor, eps, depth_clamp, bits, loss_sum, grad_boxes);
+  // The call is synchronous, like the CPU op it stands in for — and on a failure half-way the
+  // copies already enqueued still reference the caller's host buffers: drain every stream first.
+  cudaError_t e = cudaStreamSynchronize(c->box_stream);
+  for (int s = 0; s < c->n_streams; ++s) {
+    const cudaError_t es = cudaStreamSynchronize(c->streams[s]);
+    if (e == cudaSuccess) e = es;
+  }
+  if (rc != GGA_OK) return rc;
   if (e != cudaSuccess) {
     gga_set_error("gga_step_run_host: %s", cudaGetErrorString(e));
     return GGA_ERR_CUDA;

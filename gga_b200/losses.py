@@ -64,9 +64,10 @@ class _Box2DLoss(torch.autograd.Function):
         gp = torch.empty((n, 4), dtype=torch.float32, device=dev)
         gt = torch.empty((n, 4), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            sc = _lib.loss_scratch(dev)
             _lib.check(_lib.load().gga_box2d_loss(
                 _lib.ptr(p), _lib.ptr(t), _lib.ptr(w), wc, None, n, kind, float(eps), 1.0,
-                _lib.ptr(loss), _lib.ptr(loss_sum), _lib.ptr(gp), _lib.ptr(gt),
+                _lib.ptr(loss), _lib.ptr(loss_sum), _lib.ptr(gp), _lib.ptr(gt), sc.data_ptr(), sc.numel(),
                 _lib.current_stream(dev)), 'box2d_loss')
         ctx.save_for_backward(gp, gt)
         ctx.per_box = per_box
@@ -192,6 +193,8 @@ class _ProjectedBoxLoss(torch.autograd.Function):
         a.box2d, a.valid, a.loss, a.loss_sum = _lib.ptr(box2d), _lib.ptr(valid), _lib.ptr(loss), _lib.ptr(loss_sum)
         a.grad_boxes, a.grad_target = _lib.ptr(gb), _lib.ptr(gt)
         with torch.cuda.device(dev):
+            sc = _lib.loss_scratch(dev)
+            a.scratch, a.scratch_bytes = sc.data_ptr(), sc.numel()
             _lib.check(_lib.load().gga_box_project_loss(a, _lib.current_stream(dev)), 'box_project_loss')
         ctx.save_for_backward(gb, gt)
         ctx.bshape, ctx.tshape, ctx.bdtype = boxes.shape, target.shape, boxes.dtype
@@ -246,9 +249,11 @@ class _Box3DAALoss(torch.autograd.Function):
         gp = torch.empty((n, 6), dtype=torch.float32, device=dev)
         gt = torch.empty((n, 6), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            sc = _lib.loss_scratch(dev)
             _lib.check(_lib.load().gga_box3d_aa_loss(_lib.ptr(p), _lib.ptr(t), _lib.ptr(w), None, n, int(giou),
                                                      float(eps), 1.0, _lib.ptr(loss), _lib.ptr(loss_sum),
-                                                     _lib.ptr(gp), _lib.ptr(gt), _lib.current_stream(dev)),
+                                                     _lib.ptr(gp), _lib.ptr(gt), sc.data_ptr(), sc.numel(),
+                                                     _lib.current_stream(dev)),
                        'box3d_aa_loss')
         ctx.save_for_backward(gp, gt)
         ctx.per_box, ctx.shape = per_box, pred.shape

@@ -44,27 +44,6 @@ def _as_f32_rows(t):
     return t, C
 
 
-_WORKSPACES = {}
-
-
-def workspace(device, B, M, T):
-    """Scratch tensor for one membership call on the CURRENT stream of `device` (the caller of
-    the C ABI owns the scratch, include/gga_b200.h).  Cached per (device, stream) and grown on
-    demand (its previous contents never matter).  Under CUDA-graph capture a
-    private tensor is returned instead (the graph keeps it alive)."""
-    L = _lib.load()
-    nbytes = int(L.gga_pib_workspace_bytes(int(B), int(M), int(T)))
-    device = torch.device(device)
-    if torch.cuda.is_current_stream_capturing():
-        return torch.zeros((nbytes,), dtype=torch.uint8, device=device)
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
-    return ws
-
-
 def _device_check(points, boxes):
     assert points.is_cuda and boxes.is_cuda, 'points and boxes must be CUDA tensors'
     assert points.device == boxes.device, 'Points and boxes should be put on the same device'
@@ -91,9 +70,7 @@ def points_in_boxes_bits(points, boxes):
     bx = boxes.float().contiguous()
     out = torch.empty((B, M, W), dtype=torch.int32, device=points.device)
     with torch.cuda.device(points.device):
-        ws = workspace(points.device, B, M, T)
         _lib.check(L.gga_points_in_boxes_bits(_lib.ptr(pts), stride, _lib.ptr(bx), _lib.ptr(out), B, M, T,
-                                              ws.data_ptr(), ws.numel(),
                                               _lib.current_stream(points.device)), 'points_in_boxes_bits')
     return out
 
@@ -129,9 +106,7 @@ def points_in_boxes_all(points, boxes):
     bx = boxes.float().contiguous()
     out = torch.empty((B, M, T), dtype=torch.int32, device=points.device)
     with torch.cuda.device(points.device):
-        ws = workspace(points.device, B, M, T)
         _lib.check(L.gga_points_in_boxes_all(_lib.ptr(pts), stride, _lib.ptr(bx), _lib.ptr(out), B, M, T,
-                                              ws.data_ptr(), ws.numel(),
                                              _lib.current_stream(points.device)), 'points_in_boxes_all')
     return out
 
@@ -152,9 +127,7 @@ def points_in_boxes_part(points, boxes):
     bx = boxes.float().contiguous()
     out = torch.empty((B, M), dtype=torch.int32, device=points.device)
     with torch.cuda.device(points.device):
-        ws = workspace(points.device, B, M, T)
         _lib.check(L.gga_points_in_boxes_part(_lib.ptr(pts), stride, _lib.ptr(bx), _lib.ptr(out), B, M, T,
-                                              ws.data_ptr(), ws.numel(),
                                               _lib.current_stream(points.device)), 'points_in_boxes_part')
     return out
 
@@ -177,9 +150,3 @@ def points_in_boxes_cpu(points, boxes):
     _lib.check(L.gga_points_in_boxes_all_host(_lib.ptr(pts), 3, _lib.ptr(bx), _lib.ptr(out), B, M, T),
                'points_in_boxes_cpu')
     return out
-
-
-def set_tuning(grid_cells=0, ctas_per_sm=0):
-    """Overrides the box-index resolution (cells per side, upper bound) / resident CTAs per SM
-    of the streaming kernel (0 = automatic)."""
-    _lib.check(_lib.load().gga_pib_set_tuning(int(grid_cells), int(ctas_per_sm)))

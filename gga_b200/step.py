@@ -46,8 +46,9 @@ class GeometryStep:
         self.loss_sum = torch.zeros((1,), dtype=torch.float32, device=dev)
         self.loss_accum = None   # optional [1] running total shared by several steps (set by the caller)
         self.grad_boxes = torch.empty((n, 7), dtype=torch.float32, device=dev)
-        self.ws = torch.zeros((int(L.gga_pib_workspace_bytes(self.F, self.N, self.M)),), dtype=torch.uint8,
-                              device=dev)
+        # scratch of the loss reduction: owned by this step, so steps on parallel streams / graph
+        # branches never share it (include/gga_b200.h: zeroed once, the kernel leaves it zeroed)
+        self.scratch = torch.zeros((int(L.gga_loss_scratch_bytes()),), dtype=torch.uint8, device=dev)
         self.side = torch.cuda.Stream(device=dev)   # the box kernel runs beside the membership kernels
         self.graph = None
         self._host = None
@@ -63,24 +64,23 @@ class GeometryStep:
         all-reduce of the loss sum (``gga_b200.dist.reduce_scalars``), which then overlaps the
         membership kernels and is captured with them in the CUDA graph."""
         L = self.L
-        n = self.F * self.M
-        cur = torch.cuda.current_stream(self.device)
-        st = cur.cuda_stream
-        fork = torch.cuda.Event()
-        fork.record(cur)
-        self.side.wait_event(fork)
-        _lib.check(L.gga_points_in_boxes_bits(points.data_ptr(), self.pts_stride, boxes.data_ptr(),
-                                              self.bits.data_ptr(), self.F, self.N, self.M,
-                                              self.ws.data_ptr(), self.ws.numel(), st),
-                   'points_in_boxes_bits')
-        a = self._box_args(boxes, lidar2img, target, weight, avg_factor)
-        _lib.check(L.gga_box_project_loss(a, self.side.cuda_stream), 'box_project_loss')
-        if after_loss is not None:
-            with torch.cuda.stream(self.side):
-                after_loss(self)
-        join = torch.cuda.Event()
-        join.record(self.side)
-        cur.wait_event(join)
+        with torch.cuda.device(self.device):   # the C ABI works on the CURRENT device
+            cur = torch.cuda.current_stream(self.device)
+            st = cur.cuda_stream
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            self.side.wait_event(fork)
+            _lib.check(L.gga_points_in_boxes_bits(points.data_ptr(), self.pts_stride, boxes.data_ptr(),
+                                                  self.bits.data_ptr(), self.F, self.N, self.M, st),
+                       'points_in_boxes_bits')
+            a = self._box_args(boxes, lidar2img, target, weight, avg_factor)
+            _lib.check(L.gga_box_project_loss(a, self.side.cuda_stream), 'box_project_loss')
+            if after_loss is not None:
+                with torch.cuda.stream(self.side):
+                    after_loss(self)
+            join = torch.cuda.Event()
+            join.record(self.side)
+            cur.wait_event(join)
 
     def capture(self, *args, **kw):
         """Warm up, then capture ``run(*args)`` into a CUDA graph (inputs are baked in by address)."""
@@ -115,6 +115,7 @@ class GeometryStep:
         a.grad_scale = self.loss_weight / float(avg_factor if avg_factor is not None else max(n, 1))
         a.box2d, a.loss, a.loss_sum = self.box2d.data_ptr(), self.loss.data_ptr(), self.loss_sum.data_ptr()
         a.grad_boxes = self.grad_boxes.data_ptr()
+        a.scratch, a.scratch_bytes = self.scratch.data_ptr(), self.scratch.numel()
         if self.loss_accum is not None:
             a.loss_accum = self.loss_accum.data_ptr()
         return a

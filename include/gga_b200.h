@@ -50,43 +50,29 @@ int gga_device_info(int* sm_count, int* cc_major, int* cc_minor, size_t* total_m
  * Box t of a point is bit (t & 31) of word (t >> 5); padding bits are zero. */
 int gga_pib_row_words(int num_boxes);
 
-/* Scratch memory of one membership call (the per-frame box index built on the device:
- * contract terms of every box, BEV cell grid, candidate id lists).
- * The caller owns it, like every other buffer: device memory, 256-byte aligned, at least
- * gga_pib_workspace_bytes(B, num_points, num_boxes) bytes; its previous contents do not matter
- * (every call rebuilds what it reads).  A workspace must not be shared by calls that can run
- * concurrently (different streams).  gga_pib_workspace_init (a memset) is kept for callers
- * that want deterministic scratch contents. */
-size_t gga_pib_workspace_bytes(int B, int num_points, int num_boxes);
-int gga_pib_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+/* The membership calls need no scratch memory: the per-frame box index lives in shared memory
+ * of the one kernel a call launches, so concurrent calls on different streams share nothing.
+ * (mmcv's ops allocate nothing either.) */
 
 /* bits : uint32 [B, num_points, gga_pib_row_words(num_boxes)] */
 int gga_points_in_boxes_bits(const float* points, int pts_stride, const float* boxes,
-                             uint32_t* bits, int B, int num_points, int num_boxes,
-                             void* workspace, size_t workspace_bytes, void* stream);
+                             uint32_t* bits, int B, int num_points, int num_boxes, void* stream);
 
 /* out : int32 [B, num_points, num_boxes], 0/1 — exact layout of mmcv points_in_boxes_all.
  * Every element is written (no pre-zeroing needed). */
 int gga_points_in_boxes_all(const float* points, int pts_stride, const float* boxes, int32_t* out,
-                            int B, int num_points, int num_boxes, void* workspace,
-                            size_t workspace_bytes, void* stream);
+                            int B, int num_points, int num_boxes, void* stream);
 
 /* out : int32 [B, num_points], index of the first enclosing box or -1 — mmcv
  * points_in_boxes_part. */
 int gga_points_in_boxes_part(const float* points, int pts_stride, const float* boxes,
-                             int32_t* out, int B, int num_points, int num_boxes, void* workspace,
-                             size_t workspace_bytes, void* stream);
+                             int32_t* out, int B, int num_points, int num_boxes, void* stream);
 
 /* HOST buffers in and out (the points_in_boxes_cpu signature: CPU tensors), computed on
- * the current device: H2D, kernels, D2H, synchronous; scratch is allocated internally.
+ * the current device: H2D, kernel, D2H, synchronous; device buffers are allocated internally.
  * out : int32 [B, num_points, num_boxes]. */
 int gga_points_in_boxes_all_host(const float* points, int pts_stride, const float* boxes,
                                  int32_t* out, int B, int num_points, int num_boxes);
-
-/* Tuning knobs (0 = automatic): BEV index cells per side (upper bound; the device picks the
- * per-frame resolution), resident CTAs per SM of the streaming kernel.  Changing the first
- * changes gga_pib_workspace_bytes. */
-int gga_pib_set_tuning(int grid_cells, int ctas_per_sm);
 
 /* ------------------------------------------------------------------------------------
  * Part 2 + 3 — box corners -> projection -> 8-corner min/max -> (clamped) 2D box, and the
@@ -155,7 +141,18 @@ typedef struct gga_box_loss_args {
   float* grad_boxes;       /* [n, 7] d(total)/d(boxes) */
   float* grad_box2d;       /* [n, 4] d(total)/d(box2d) */
   float* grad_target;      /* [n, 4] d(total)/d(target) (PGD passes a prediction as target) */
+  /* scratch of the deterministic reduction behind loss_sum (required iff loss_sum != NULL) */
+  void* scratch;
+  size_t scratch_bytes;
 } gga_box_loss_args;
+
+/* Scratch of the loss reductions (gga_box_project_loss, gga_box2d_loss, gga_box3d_aa_loss with a
+ * non-NULL loss_sum): caller-owned device memory, 16-byte aligned, at least
+ * gga_loss_scratch_bytes() bytes, ZEROED ONCE by the caller before its first use (the kernels
+ * leave it zeroed).  Calls that can run concurrently (different streams, parallel graph
+ * branches) must use different scratch buffers; calls ordered on one stream may share one.
+ * The library itself keeps no device state. */
+size_t gga_loss_scratch_bytes(void);
 
 int gga_box_project_loss(const gga_box_loss_args* args, void* stream);
 
@@ -169,7 +166,8 @@ int gga_box_project_backward(const float* boxes, const float* proj, int proj_str
 /* 2D loss on given boxes (no projection): per-box loss, weighted sum, gradients. */
 int gga_box2d_loss(const float* pred, const float* target, const float* weight, int weight_cols,
                    const float* grad_loss, int n, int loss_kind, float eps, float grad_scale,
-                   float* loss, float* loss_sum, float* grad_pred, float* grad_target, void* stream);
+                   float* loss, float* loss_sum, float* grad_pred, float* grad_target,
+                   void* scratch, size_t scratch_bytes, void* stream);
 
 /* Axis-aligned 3-D IoU (giou = 0) / GIoU (giou = 1) loss of aligned pairs, boxes [n, 6] =
  * (x1, y1, z1, x2, y2, z2): AxisAlignedIoULoss, /root/reference/mmdet3d/models/losses/
@@ -178,7 +176,8 @@ int gga_box2d_loss(const float* pred, const float* target, const float* weight, 
  * (fcaf3d_head.py:59,313-318).  loss = 1 - iou; weight [n] or NULL; outputs as gga_box2d_loss. */
 int gga_box3d_aa_loss(const float* pred, const float* target, const float* weight,
                       const float* grad_loss, int n, int giou, float eps, float grad_scale,
-                      float* loss, float* loss_sum, float* grad_pred, float* grad_target, void* stream);
+                      float* loss, float* loss_sum, float* grad_pred, float* grad_target,
+                      void* scratch, size_t scratch_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Matching — block-diagonal pairwise 2D IoU + argmax (pseudo-label matching).
@@ -337,14 +336,6 @@ int gga_step_device_bits(void* ctx, uint32_t** bits_device);
 /* ------------------------------------------------------------------------------------
  * Test hooks (device build of include/gga_detmath.h and of the per-box preparation).
  * ---------------------------------------------------------------------------------- */
-/* profiling hook: 0 = both membership kernels, 1 = index build only, 2 = streaming only
- * (reuses the index already in the workspace; results are only valid for phase 0) */
-int gga_test_pib_phase(int phase);
-/* profiling hook: device buffer receiving 16 x uint64 per warp of the streaming kernel
- * (globaltimer stamps; word 15 = SM id); NULL switches tracing off */
-int gga_test_pib_trace(void* device_buffer);
-/* same for the index-build kernel: 16 stamps per CTA, one per phase boundary */
-int gga_test_pib_trace_prep(void* device_buffer);
 int gga_test_sincos(const float* x, int64_t n, float* sn, float* cs, void* stream);
 /* prep : float [num_boxes, 8] = (cx, cy, cz_centre, hz, cosa, sina, hx, hy) */
 int gga_test_box_prep(const float* boxes, int num_boxes, float* prep, void* stream);

@@ -104,6 +104,63 @@ GGA_HD double gga_kcos(double x, double y) {
   return GGA_DADD(w, t);
 }
 
+GGA_HD uint64_t gga_d2bits(double d) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(d);
+#else
+  union { uint64_t u; double d; } c; c.d = d; return c.u;
+#endif
+}
+
+/* 1 when rounding the double `d` to fp32 cannot be changed by an error of 256 double ulps,
+ * i.e. the 29 dropped mantissa bits are not within 256 of the round-to-nearest midpoint. */
+GGA_HD int gga_f32_rounding_is_safe(double d) {
+  const uint32_t low = (uint32_t)(gga_d2bits(d) & 0x1fffffffull);
+  const uint32_t dist = low > 0x10000000u ? low - 0x10000000u : 0x10000000u - low;
+  return dist > 256u;
+}
+
+/* Fast path for pi/4 < |x| < 64 (every yaw a detector produces): two-constant Cody-Waite
+ * reduction of |x| in double-double instead of the 192-bit Payne-Hanek product.  Both paths
+ * feed the same kernels and are accurate to ~1e-15 relative, so they round to the same fp32
+ * unless the result sits within 256 double ulps of an fp32 rounding midpoint (or the reduced
+ * argument is tiny); those inputs (about 1e-6 of them) return 0 and take the full path.  The
+ * fp32 results are therefore identical by construction; `oracle/check_sincos.c` re-checks
+ * every fp32 input against libm.
+ *   k = rint(|x| * 2/pi) <= 41;  r = |x| - k*P1 (exact: P1 has 33 bits);  w = k*P1T;
+ *   (rh, rl) = TwoSum(r, -w). */
+GGA_HD int gga_sincos_small(uint32_t abits, double* sn, double* cs) {
+#if defined(__CUDA_ARCH__)
+  const double ax = (double)__uint_as_float(abits);
+#else
+  union { uint32_t u; float f; } cv; cv.u = abits;
+  const double ax = (double)cv.f;
+#endif
+  const double INVPIO2 = 6.36619772367581382433e-01, P1 = 1.57079632673412561417e+00,
+               P1T = 6.07710050650619224932e-11, MAGIC = 6755399441055744.0; /* 1.5 * 2^52 */
+  const double fn = GGA_DSUB(GGA_DADD(GGA_DMUL(ax, INVPIO2), MAGIC), MAGIC);
+  const double r = GGA_DSUB(ax, GGA_DMUL(fn, P1));
+  const double nw = -GGA_DMUL(fn, P1T);
+  const double rh = GGA_DADD(r, nw);
+  const double bb = GGA_DSUB(rh, r);
+  const double rl = GGA_DADD(GGA_DSUB(r, GGA_DSUB(rh, bb)), GGA_DSUB(nw, bb));
+  const double arh = rh < 0.0 ? -rh : rh;
+  if (!(arh > 9.5367431640625e-07)) return 0; /* |r| <= 2^-20: cancellation, use the exact reduction */
+  const double ks = gga_ksin(rh, rl), kc = gga_kcos(rh, rl);
+  if (!gga_f32_rounding_is_safe(ks) || !gga_f32_rounding_is_safe(kc)) return 0;
+  const uint32_t q = (uint32_t)(int32_t)fn;
+  double s, c;
+  switch (q & 3u) {
+    case 0: s = ks; c = kc; break;
+    case 1: s = kc; c = -ks; break;
+    case 2: s = -ks; c = -kc; break;
+    default: s = -kc; c = ks; break;
+  }
+  *sn = s;
+  *cs = c;
+  return 1;
+}
+
 /* sin and cos of an fp32 angle, evaluated in double.  Results are doubles with
  * < 1 ulp error; the membership contract rounds them to fp32. */
 GGA_HD void gga_sincos_f32(float xf, double* sn, double* cs) {
@@ -124,6 +181,14 @@ GGA_HD void gga_sincos_f32(float xf, double* sn, double* cs) {
     *sn = gga_ksin(rh, rl);
     *cs = gga_kcos(rh, rl);
     return;
+  }
+  if (abits < 0x42800000u) { /* |x| < 64: Cody-Waite reduction, falls through when the result is too close to call */
+    double fs, fc;
+    if (gga_sincos_small(abits, &fs, &fc)) {
+      *sn = negx ? -fs : fs;
+      *cs = fc;
+      return;
+    }
   }
   /* 32 zero bits followed by the first 352 bits of 2/pi, most significant word first. */
   const uint64_t T0 = 0x00000000a2f9836eull, T1 = 0x4e441529fc2757d1ull,

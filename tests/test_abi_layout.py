@@ -62,13 +62,13 @@ int main(int argc, char** argv) {
   if (!h) { fprintf(stderr, "%%s\n", dlerror()); return 2; }
   int (*version)(void) = (int (*)(void))dlsym(h, "gga_version");
   int (*row_words)(int) = (int (*)(int))dlsym(h, "gga_pib_row_words");
-  size_t (*ws_bytes)(int, int, int) = (size_t (*)(int, int, int))dlsym(h, "gga_pib_workspace_bytes");
-  int (*bits)(const float*, int, const float*, uint32_t*, int, int, int, void*, size_t, void*) =
-      (int (*)(const float*, int, const float*, uint32_t*, int, int, int, void*, size_t, void*))dlsym(h, "gga_points_in_boxes_bits");
+  size_t (*ws_bytes)(void) = (size_t (*)(void))dlsym(h, "gga_loss_scratch_bytes");
+  int (*bits)(const float*, int, const float*, uint32_t*, int, int, int, void*) =
+      (int (*)(const float*, int, const float*, uint32_t*, int, int, int, void*))dlsym(h, "gga_points_in_boxes_bits");
   const char* (*last_error)(void) = (const char* (*)(void))dlsym(h, "gga_last_error");
   if (!version || !row_words || !ws_bytes || !bits || !last_error) return 3;
-  int rc = bits(NULL, 2, NULL, NULL, 1, 8, 8, NULL, 0, NULL);   /* pts_stride < 3: rejected before any CUDA call */
-  printf("%%d %%d %%d %%zu %%d %%s\n", version(), row_words(256), row_words(1024), ws_bytes(8, 120000, 256), rc, last_error());
+  int rc = bits(NULL, 2, NULL, NULL, 1, 8, 8, NULL);   /* pts_stride < 3: rejected before any CUDA call */
+  printf("%%d %%d %%d %%zu %%d %%s\n", version(), row_words(256), row_words(1024), ws_bytes(), rc, last_error());
   return 0;
 }
 ''' % HEADER

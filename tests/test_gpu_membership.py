@@ -231,16 +231,34 @@ def test_config_shapes_bit_exact(cfg, frames):
         assert ref.any(1).mean() > 0.05
 
 
-def test_tuning_knobs_do_not_change_results():
-    f = synth.make_frame(2, 7, N=30000)
-    ref = om.points_in_boxes_all_np(f['points'], f['boxes'], 8)
-    P, B = cu(f['points'])[None], cu(f['boxes'])[None]
-    try:
-        for g, c in [(1, 1), (3, 5), (16, 0), (64, 37), (128, 104), (0, -5), (96, -2)]:  # c < 0: never the shared-memory-grid stream variant
-            G.ops.set_tuning(g, c)
-            assert np.array_equal(G.unpack_bits(G.points_in_boxes_bits(P, B), 256)[0].cpu().numpy(), ref)
-    finally:
-        G.ops.set_tuning(0, 0)
+@pytest.mark.parametrize('T,N', [(8000, 700), (32768 + 5, 300)])
+def test_many_boxes_are_served_in_chunks(T, N):
+    """More boxes than one sweep indexes (1024): the mmcv op accepts any T, so does this one."""
+    rng = np.random.default_rng(T)
+    boxes = synth.make_boxes(rng, T)
+    pts = synth.make_points(rng, N, boxes[:2000])
+    ref = om.points_in_boxes_all_np(pts[:, :3], boxes, nthreads=8)
+    P, B = cu(pts)[None], cu(boxes)[None]
+    assert np.array_equal(G.unpack_bits(G.points_in_boxes_bits(P, B), T)[0].cpu().numpy(), ref)
+    part = G.points_in_boxes_part(P[..., :3], B)[0].cpu().numpy()
+    assert np.array_equal(part, np.where(ref.any(1), ref.argmax(1), -1))
+    if T <= 8000:
+        assert np.array_equal(G.points_in_boxes_all(P[..., :3], B)[0].cpu().numpy(), ref)
+
+
+def test_extreme_extents_keep_the_index_conservative():
+    """Box extents spanning many orders of magnitude (one far-away box stretches the bin grid so
+    that every other box shares a bin) and points outside every bin."""
+    rng = np.random.default_rng(123)
+    boxes = synth.make_boxes(rng, 200)
+    boxes[0, :2] = [5e6, -7e6]
+    boxes[1, :2] = [-3e7, 2e7]
+    boxes[2, 3:5] = [1e5, 3e4]
+    pts = synth.make_points(rng, 6000, boxes)
+    pts[:50, :2] = rng.uniform(-1e7, 1e7, (50, 2))
+    pts[50:60, :3] = boxes[:10, :3] + [0, 0, 0.5]
+    ref = check_against_oracle(pts, boxes)
+    assert ref[50:60].any()
 
 
 def test_full_size_stress_properties():

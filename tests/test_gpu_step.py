@@ -77,27 +77,93 @@ def test_step_matches_oracle_eager_graph_and_host():
                          masks_to_host=False)[1] == F * M * 7 * 4 + 4
 
 
-def test_workspace_contract_unzeroed_and_shared_sizes():
-    """A workspace that was never zeroed must still give exact results (the id-pool cursor
-    then overflows into the 'every box' fallback) and leaves itself clean for the next call."""
-    f = synth.make_frame(3, 2, N=4000)                       # dense SUN-RGBD-like scene, 512 boxes
+def test_membership_needs_no_scratch_and_is_repeatable():
+    """The membership call owns no global scratch: the same call twice into a poisoned output
+    buffer gives the same exact rows (dense SUN-RGBD-like scene, 512 boxes = 16-word rows)."""
+    f = synth.make_frame(3, 2, N=4000)
     ref = om.points_in_boxes_all_np(f['points'], f['boxes'], 8)
     P, B = torch.from_numpy(f['points']).cuda()[None], torch.from_numpy(f['boxes']).cuda()[None]
     L = G._lib.load()
-    nbytes = int(L.gga_pib_workspace_bytes(1, 4000, 512))
-    ws = torch.full((nbytes,), 0xAB, dtype=torch.uint8, device='cuda')
     out = torch.empty((1, 4000, G.row_words(512)), dtype=torch.int32, device='cuda')
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):
         out.fill_(-1)
-        G._lib.check(L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512,
-                                                ws.data_ptr(), ws.numel(), st))
+        G._lib.check(L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512, st))
         assert np.array_equal(G.unpack_bits(out, 512)[0].cpu().numpy(), ref)
-    # too small / misaligned workspaces are rejected, not overrun
-    assert L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512,
-                                      ws.data_ptr(), 1024, st) == -1
-    assert L.gga_points_in_boxes_bits(P.data_ptr(), 4, B.data_ptr(), out.data_ptr(), 1, 4000, 512,
-                                      ws.data_ptr() + 4, ws.numel() - 4, st) == -1
+
+
+def test_loss_scratch_contract():
+    """loss_sum needs caller-owned scratch: missing / too small / misaligned scratch is rejected."""
+    L = G._lib.load()
+    n = 64
+    p = torch.rand((n, 4), device='cuda')
+    p[:, 2:] += p[:, :2]
+    t = p.clone()
+    ls = torch.zeros((1,), device='cuda')
+    sc = torch.zeros((int(L.gga_loss_scratch_bytes()),), dtype=torch.uint8, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    args = (p.data_ptr(), t.data_ptr(), None, 1, None, n, G._lib.LOSS_GIOU, 1e-6, 1.0, None, ls.data_ptr(), None, None)
+    assert L.gga_box2d_loss(*args, None, 0, st) == -1
+    assert L.gga_box2d_loss(*args, sc.data_ptr(), 128, st) == -1
+    assert L.gga_box2d_loss(*args, sc.data_ptr() + 4, sc.numel() - 4, st) == -1
+    for _ in range(3):   # the kernel leaves the scratch zeroed: reusable without re-initialisation
+        assert L.gga_box2d_loss(*args, sc.data_ptr(), sc.numel(), st) == 0
+        torch.cuda.synchronize()
+        assert abs(float(ls)) < 1e-6
+    assert int(sc[:4].view(torch.int32)) == 0
+
+
+def test_concurrent_steps_do_not_share_state():
+    """Two steps replayed from parallel graph branches and from two host threads at once give
+    the loss sums of the sequential runs (each GeometryStep owns its reduction scratch)."""
+    import threading
+    F, N, M = 2, 3000, 300
+    steps, sets, want = [], [], []
+    for k in range(4):
+        bt = synth.make_batch(2, 50 + 3 * k, F, N=N, M=M)
+        t = {n_: torch.from_numpy(np.ascontiguousarray(v)).cuda() for n_, v in bt.items()}
+        s = GeometryStep(F, N, M, 'cuda', kind='giou', mode='lidar_direct')
+        s.run(t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
+        torch.cuda.synchronize()
+        want.append((float(s.loss_sum), s.bits.clone(), s.grad_boxes.clone()))
+        steps.append(s)
+        sets.append(t)
+    streams = [torch.cuda.Stream() for _ in steps]
+
+    def worker(i):
+        with torch.cuda.stream(streams[i]):
+            for _ in range(20):
+                t = sets[i]
+                steps[i].run(t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
+    th = [threading.Thread(target=worker, args=(i,)) for i in range(len(steps))]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    torch.cuda.synchronize()
+    for s, (ls, bits, gb) in zip(steps, want):
+        assert float(s.loss_sum) == ls and torch.equal(s.bits, bits) and torch.equal(s.grad_boxes, gb)
+    # the same four steps as parallel branches of one CUDA graph, replayed several times
+    g = torch.cuda.CUDAGraph()
+    for s in steps:
+        s.loss_sum.zero_()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        cur = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        for i, s in enumerate(steps):
+            streams[i].wait_event(fork)
+            with torch.cuda.stream(streams[i]):
+                t = sets[i]
+                for _ in range(3):
+                    s.run(t['points'], t['boxes'], t['lidar2img'], t['target'], t['weight'], float(F * M))
+            cur.wait_stream(streams[i])
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    for s, (ls, bits, gb) in zip(steps, want):
+        assert float(s.loss_sum) == ls and torch.equal(s.bits, bits) and torch.equal(s.grad_boxes, gb)
 
 
 @pytest.mark.parametrize('T,N,B', [(1, 777, 1), (33, 1000, 2), (1500, 3000, 1), (5000, 1200, 1), (16, 300, 200)])
