@@ -34,7 +34,18 @@ namespace {
 
 constexpr int kBins = 128;         // bins per axis (126 inner bins tile the boxes' extent, 2 border bins)
 constexpr int kChunkBoxes = 1024;  // boxes indexed per sweep = 32 row words
-constexpr int kDepth = 3;          // point batches in flight per warp (the sweep loop is written for 3)
+constexpr int kTileBatches = 8;    // point tile of the shared-memory ring: 8 batches = 256 points
+constexpr int kMaxSlots = 56;      // ring slots (tiles) a CTA can hold
+// Cell table of the sparse path (at most 256 boxes): kCellsSide^2 cells of 2 x 2 bins, each an 8-byte
+// entry with the ids (one byte each) of up to 7 boxes whose rectangle touches the cell and their count.
+// A slot is claimed with an atomicAdd on the count; shared-memory atomics that return a value have
+// several hundred cycles of latency (measured), so ALL threads of the CTA share the insertions
+// (4 threads per box at 256 boxes, four cells in flight per thread).
+constexpr int kCellsSide = kBins / 2;
+constexpr int kCellIds = 7;
+constexpr int kWideCells = 256;  // a box covering more cells is kept in a short list tested for every point
+constexpr int kMaxWide = 8;
+__host__ __device__ __forceinline__ int cell_of_bin(int b) { return b >> 1; }
 
 enum { kModeBits = 0, kModeAll = 1, kModePart = 2 };
 
@@ -114,11 +125,11 @@ struct SweepParams {
   const float* boxes;   // [B, T, 7]
   void* out;            // bits: uint32 [B, N, W]; all: int32 [B, N, T]; part: int32 [B, N]
   int pts_stride, N, T, B;
-  int W;        // words per row of the bit-packed layout (also sizes the shared-memory tables)
-  int bpf;      // 32-point batches per frame
-  int rf;       // CTAs per frame = gridDim.x; CTA r serves batches r, r + rf, r + 2 rf, ... of its frame
-  int nchunks;  // sweeps over the box list (1024 boxes each)
-  unsigned long long* trace;  // GGA_PROFILING builds: 16 globaltimer stamps per CTA (NULL = off)
+  int W;           // words per row of the bit-packed layout (also sizes the shared-memory tables)
+  int bpf;         // 32-point batches per frame
+  int nchunks;     // sweeps over the box list (1024 boxes each)
+  int ring_slots;  // point tiles the shared-memory ring holds (0: points are loaded directly)
+  unsigned long long* trace;  // GGA_PROFILING builds: 16 globaltimer stamps per warp (NULL = off)
   int variant;                // GGA_PROFILING builds: experiment switches (0 in the product)
 };
 
@@ -134,41 +145,78 @@ __device__ __forceinline__ int bin_of(float v, float inv, float off) {
   return (int)fmaxf(fminf(__fmaf_rn(v, inv, off), (float)(kBins - 1)), 0.f);
 }
 
-// Bulk asynchronous store shared -> global (TMA, 1-D): one lane hands a warp's finished rows to
-// the copy engine, so the rows cross the load/store unit once (the STS that built them) instead of
-// three times (STS, LDS, STG) — the kernel is bound by LSU wavefronts, not by issue slots or DRAM.
+// ---- bulk asynchronous copies (TMA, 1-D) and their mbarriers -------------------------------------
+// Points enter through a shared-memory ring filled by cp.async.bulk (one elected lane requests 4 KB
+// tiles; the whole share of a CTA is in flight from the first microsecond: the sweep of a
+// training-shape launch lasts only a few DRAM latencies, so register prefetch of 2-3 batches per
+// warp left it latency bound) and finished rows leave through cp.async.bulk as well, so they cross
+// the load/store unit once (the STS that built them) instead of three times (STS, LDS, STG).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
-               "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// MODE: output layout.  WC: row words of a sweep known at compile time (1, 2, 4, 8) or 0 = a
-// multiple of 8 taken from the params (up to 32).  NT: threads per CTA.  VEC4: 16-byte points.
+// MODE: output layout.  WC: row words of a sweep known at compile time (1, 2, 4, 8: at most 256
+// boxes, the sparse path) or 0 = a multiple of 8 taken from the params (up to 32).  NT: threads per
+// CTA.  VEC4: 16-byte points.
 template <int MODE, int WC, int NT, bool VEC4>
 __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
   constexpr int kWarps = NT / 32;
-  constexpr int KB = (kChunkBoxes + NT - 1) / NT;  // box jobs per thread in the index build
-  constexpr bool kWide = (WC == 0 || WC >= 4);     // rows of whole 16-byte chunks
+  constexpr int KB = (kChunkBoxes + NT - 1) / NT;     // box jobs per thread in the index build
+  constexpr bool kWide = (WC == 0 || WC >= 4);        // rows of whole 16-byte chunks
   constexpr bool kBulk = MODE == kModeBits && kWide;  // rows can leave through the bulk copy engine
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool kCells = WC != 0;                    // <= 256 boxes: candidates come from the cell table
+  constexpr int kStages = kBulk && WC != 0 ? 2 : 1;   // stage buffers per warp (narrow rows: double buffered)
+  constexpr int R = kWarps / kTileBatches;            // point tiles consumed at a time (8 warps per tile)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint32_t s_wext[kWarps][4];  // per-warp extent of the finite box rectangles
   __shared__ float s_bin[4];              // bin function of the sweep: invx, offx, invy, offy
+  __shared__ int s_flags[2];              // [0] some cell holds more than kCellIds boxes (axis masks needed), [1] cells unusable
+  __shared__ int s_nwide;
+  __shared__ int s_wide[kMaxWide];
+  __shared__ uint32_t s_rect[kCells ? 256 : 1];  // bin rectangle of every box (sparse path), 4 x 8 bits
+  __shared__ __align__(8) unsigned long long s_full[kMaxSlots], s_empty[kMaxSlots];
 
   // Programmatic dependent launch: the next kernel of the stream may become resident as this one
-  // drains.  Everything that touches no global memory (parameters, addresses, zeroed tables) runs
-  // BEFORE the wait and so overlaps the previous kernel's tail; nothing is read or written in
-  // global memory before the previous kernel of the stream has completed and flushed.
+  // drains.  Everything that touches no global memory (parameters, addresses, zeroed tables,
+  // barrier set-up) runs BEFORE the wait and so overlaps the previous kernel's tail; nothing is
+  // read or written in global memory before the previous kernel of the stream has completed.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rf = gridDim.x, rr = blockIdx.x;
-  const int step = rf * kWarps;  // batches between two batches of one warp
   const int bpf = p.bpf, N = p.N;
+  const int tr = warp >> 3, tj = warp & 7;  // this warp serves batch tj of the tiles tr, tr + R, ...
   int tk = 0;
   auto stamp = [&]() {  // GGA_PROFILING: 16 globaltimer stamps per warp
 #ifdef GGA_PROFILING
@@ -189,12 +237,30 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
   uint32_t* my = mx + kBins * mcap;
   // per-warp stage: the linear image of the 32 rows of a batch; two buffers when the rows leave
   // through the bulk copy engine (one is being read by it while the next batch is built)
-  uint32_t* stage_base = my + kBins * mcap + warp * ((kBulk ? 2 : 1) * 32 * wcap);
-  auto zero_tables = [&]() {
+  uint32_t* stage_all = my + kBins * mcap;
+  uint32_t* stage_base = stage_all + warp * (kStages * 32 * wcap);
+  uint32_t* cells = stage_all + kWarps * (kStages * 32 * wcap);  // [kCellsSide^2][2] (sparse path only)
+  unsigned char* ring = reinterpret_cast<unsigned char*>(cells + (kCells ? kCellsSide * kCellsSide * 2 : 0));
+  const uint32_t tile_bytes = 1024u * (uint32_t)p.pts_stride;  // 256 points
+  const int S = p.ring_slots / R;                              // ring slots of this warp group
+  auto reset_tables = [&](bool again) {
     for (int i = tid; i < (2 * kBins * mcap) >> 2; i += NT) reinterpret_cast<uint4*>(mx)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if constexpr (kCells) {
+      for (int i = tid; i < (kCellsSide * kCellsSide * 2) >> 2; i += NT) reinterpret_cast<uint4*>(cells)[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (tid == 0) { s_flags[0] = 0; s_flags[1] = 0; s_nwide = 0; }
+    }
+    if (tid < p.ring_slots) {
+      if (again) {
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[tid])) : "memory");
+        asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_empty[tid])) : "memory");
+      }
+      mbar_init(&s_full[tid], 1u);
+      mbar_init(&s_empty[tid], (uint32_t)kTileBatches);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   };
-  zero_tables();
-  __syncthreads();  // tables zeroed
+  reset_tables(false);
+  __syncthreads();
   asm volatile("griddepcontrol.wait;" ::: "memory");
   stamp();
 
@@ -217,22 +283,45 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
       const int wc = WC > 0 ? WC : min(32, p.W - 32 * ch);
       const int ms = mask_stride(wc);
       if (!first) {
-        __syncthreads();  // the previous sweep is done with the tables
-        zero_tables();
+        __syncthreads();  // the previous sweep is done with the tables and the ring
+        reset_tables(true);
         __syncthreads();
       }
       first = false;
 
+      // ---- point tiles: CTA r of a frame serves the 256-point tiles r, r + rf, ...; a group of 8
+      //      warps consumes one tile (a batch each), the group's warp 0 / lane 0 requests its tiles
+      const int ntiles = (bpf + kTileBatches - 1) / kTileBatches;
+      const bool ring_ok = S > 0 && (reinterpret_cast<uintptr_t>(pts) & 15u) == 0;
+      const int n_full = ring_ok ? (N >> 8) : 0;  // whole tiles go through the ring, a ragged last one is loaded directly
+      auto request_tile = [&](int k, int slot) {  // k-th tile of this warp group into ring slot `slot`
+        const int ft = rr + rf * (tr + R * k);
+        if (ft < n_full) {
+          mbar_expect_tx(&s_full[slot], tile_bytes);
+          bulk_load(ring + (size_t)slot * tile_bytes, reinterpret_cast<const unsigned char*>(pts) + (size_t)ft * tile_bytes,
+                    tile_bytes, &s_full[slot]);
+        }
+      };
+      // The first tile of every warp group is requested right away; the rest of the ring once the
+      // boxes have arrived (they are the head of the index build's dependent chain and would
+      // otherwise queue behind ~100 KB of point tiles per SM in the memory system).
+      auto request_rest = [&]() {
+#ifdef GGA_PROFILING
+        if (p.variant & 512) return;
+#endif
+        if (tj == 0 && lane == 0)
+          for (int k = 1; k < S; ++k) request_tile(k, tr + R * k);
+      };
+      if (tj == 0 && lane == 0 && S > 0) request_tile(0, tr);
+
       // ---- index build -------------------------------------------------------------------
-      // Box job j (rectangle, extent, mask fill) belongs to thread j mod NT.  The exact contract
-      // terms of box j (double precision, ~0.7 us) are computed by thread (j + eoff) mod NT: when
-      // the boxes occupy at most half of the CTA, other warps do that concurrently.
+      // Box job j (rectangle, extent) belongs to thread j mod NT.  The exact contract terms of box j
+      // (double precision, ~0.7 us) are computed by thread (j + eoff) mod NT: when the boxes occupy
+      // at most half of the CTA, other warps do that concurrently.
       const int nbw = (min(Tc, NT) + 31) >> 5;  // warps holding box jobs
       const int eoff = 2 * nbw <= kWarps ? 32 * nbw : 0;
       const float* __restrict__ fb = p.boxes + ((size_t)f * p.T + t0) * 7;
       const bool box_warp = warp < nbw, terms_warp = eoff == 0 ? box_warp : (warp >= nbw && warp < 2 * nbw);
-      // the boxes are the head of the dependent chain (DRAM latency): requested first, and the
-      // warps that work on them request their points only afterwards
       float bq[KB][7];
       if (box_warp || terms_warp) {
         const int e = eoff != 0 && !box_warp ? tid - eoff : tid;
@@ -243,17 +332,6 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
           for (int j = 0; j < 7; ++j) bq[k][j] = __ldg(b + j);
         }
       }
-      // three point batches per warp in flight, in three NAMED registers: the sweep loop is unrolled
-      // by three so that no register is copied while its load is pending (a rotating array would
-      // wait for the load it just issued)
-      int g = rr + rf * warp;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
-      auto prefetch = [&]() {
-        if (g < bpf) v0 = load_pt(g);
-        if (g + step < bpf) v1 = load_pt(g + step);
-        if (g + 2 * step < bpf) v2 = load_pt(g + 2 * step);
-      };
-      if (!(box_warp || terms_warp)) prefetch();
       stamp();
       float invx = 0.f, invy = 0.f, offx = 1.f, offy = 1.f;
       auto exact_terms = [&]() {
@@ -268,11 +346,10 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
           }
         }
       };
+      int bx0[KB], bx1[KB], by0[KB], by1[KB], kind[KB];
       if (box_warp) {
-        // the box warps: rectangles, extent, mask fill; they synchronise among themselves on named
-        // barrier 1, everybody else only joins the final barrier
+        // the box warps: rectangles and extent; they synchronise among themselves on named barrier 1
         float rx0[KB], rx1[KB], ry0[KB], ry1[KB];
-        int kind[KB];
         uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mxx = 0u, mxy = 0u;
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
@@ -298,6 +375,7 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
         mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
         if (lane == 0) { s_wext[warp][0] = mnx; s_wext[warp][1] = mny; s_wext[warp][2] = mxx; s_wext[warp][3] = mxy; }
         asm volatile("bar.sync 1, %0;" ::"r"(32 * nbw) : "memory");  // warp extents published
+        request_rest();
         stamp();
         // bin function of this sweep: the inner bins tile the bounding rectangle of the finite box
         // rectangles; any non-negative scale is valid (points and boxes share it)
@@ -320,32 +398,95 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
         if (tid == 0) { s_bin[0] = invx; s_bin[1] = offx; s_bin[2] = invy; s_bin[3] = offy; }
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
-          if (kind[k] == 0) continue;
-          const int t = tid + k * NT;
-          int bx0 = 0, bx1 = kBins - 1, by0 = 0, by1 = kBins - 1;
+          bx0[k] = 0; bx1[k] = kBins - 1; by0[k] = 0; by1[k] = kBins - 1;
           if (kind[k] == 1) {
-            bx0 = bin_of(rx0[k], invx, offx); bx1 = bin_of(rx1[k], invx, offx);
-            by0 = bin_of(ry0[k], invy, offy); by1 = bin_of(ry1[k], invy, offy);
+            bx0[k] = bin_of(rx0[k], invx, offx); bx1[k] = bin_of(rx1[k], invx, offx);
+            by0[k] = bin_of(ry0[k], invy, offy); by1[k] = bin_of(ry1[k], invy, offy);
           }
-          const uint32_t bit = 1u << (t & 31);
-          uint32_t* cx_ = mx + (t >> 5);
-          uint32_t* cy_ = my + (t >> 5);
-          for (int b = bx0; b <= bx1; ++b) atomicOr(cx_ + b * ms, bit);
-          for (int b = by0; b <= by1; ++b) atomicOr(cy_ + b * ms, bit);
+          if constexpr (kCells) {
+            const int t = tid + k * NT;
+            if (t < Tc)  // an empty rectangle is stored as x0 > x1
+              s_rect[t] = kind[k] == 0 ? 1u : ((uint32_t)bx0[k] | ((uint32_t)bx1[k] << 8) | ((uint32_t)by0[k] << 16) | ((uint32_t)by1[k] << 24));
+          }
         }
-        stamp();
-        prefetch();
-        if (eoff == 0) exact_terms();
-      } else {
-        stamp();
-        if (terms_warp) {
-          exact_terms();  // concurrently with the box warps (they fit beside them)
-          prefetch();
+      }
+      if (!box_warp) {
+        if (terms_warp) {  // the boxes this warp needs have arrived once their first value is usable
+          if (__float_as_uint(bq[0][6]) == 0x7fc12345u) s_bin[0] = 0.f;  // (never true: orders the request after the load)
         }
+        request_rest();
+        if (terms_warp && eoff != 0) exact_terms();  // concurrently with the box warps (they fit beside them)
         stamp();
       }
-      __syncthreads();
+      bool need_masks = true;
+      if constexpr (kCells) {
+        // sparse path: every box appends its id to the cells (2 x 2 bins) its rectangle touches; the
+        // (box, cell row) pairs are spread over ALL threads: 2^lp threads per box, strided rows
+        __syncthreads();  // rectangles published (and the exact terms done)
+        stamp();
+        int lp = 0;
+        while (lp < 3 && (Tc << (lp + 1)) <= NT) ++lp;
+        const int P = 1 << lp;
+        for (int u = tid; u < (Tc << lp); u += NT) {
+          const uint32_t t = (uint32_t)(u >> lp);
+          const int part = u & (P - 1);
+          const uint32_t rc = s_rect[t];
+          if ((rc & 0xffu) > ((rc >> 8) & 0xffu)) continue;
+          const int cx0 = cell_of_bin((int)(rc & 0xffu)), cx1 = cell_of_bin((int)((rc >> 8) & 0xffu));
+          const int cy0 = cell_of_bin((int)((rc >> 16) & 0xffu)), cy1 = cell_of_bin((int)(rc >> 24));
+          if ((cx1 - cx0 + 1) * (cy1 - cy0 + 1) > kWideCells) {  // a few huge boxes: a short list tested for every point
+            if (part == 0) {
+              const int sl = atomicAdd(&s_nwide, 1);
+              if (sl < kMaxWide) s_wide[sl] = (int)t;
+              else s_flags[1] = 1;
+            }
+            continue;
+          }
+          for (int cy = cy0 + part; cy <= cy1; cy += P) {
+            uint32_t* rowp = cells + 2 * (cy * kCellsSide);
+            for (int cx = cx0; cx <= cx1; cx += 4) {
+              uint32_t sl[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)  // the count lives in the top byte of word 1; four cells in flight
+                sl[j] = cx + j <= cx1 ? atomicAdd(rowp + 2 * (cx + j) + 1, 1u << 24) >> 24 : 0u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (cx + j > cx1) continue;
+                uint32_t* e = rowp + 2 * (cx + j);
+                if (sl[j] < 4u) atomicOr(e, t << (8u * sl[j]));
+                else if (sl[j] < (uint32_t)kCellIds) atomicOr(e + 1, t << (8u * (sl[j] - 4u)));
+                else s_flags[0] = 1;
+                if (sl[j] >= 254u) s_flags[1] = 1;  // the one-byte count is about to wrap: do not trust the cells
+              }
+            }
+          }
+        }
+        stamp();
+        __syncthreads();
+        need_masks = (s_flags[0] | s_flags[1]) != 0;  // dense spots fall back to the axis masks
+      }
+      if (box_warp) {
+        if (need_masks) {
+#pragma unroll
+          for (int k = 0; k < KB; ++k) {
+            if (kind[k] == 0) continue;
+            const int t = tid + k * NT;
+            const uint32_t bit = 1u << (t & 31);
+            uint32_t* cx_ = mx + (t >> 5);
+            uint32_t* cy_ = my + (t >> 5);
+            for (int b = bx0[k]; b <= bx1[k]; ++b) atomicOr(cx_ + b * ms, bit);
+            for (int b = by0[k]; b <= by1[k]; ++b) atomicOr(cy_ + b * ms, bit);
+          }
+        }
+        stamp();
+        if (eoff == 0) exact_terms();
+      }
+      if (!kCells || need_masks || eoff == 0) __syncthreads();  // (all three conditions are CTA-uniform)
       invx = s_bin[0]; offx = s_bin[1]; invy = s_bin[2]; offy = s_bin[3];
+#ifdef GGA_PROFILING
+      if ((p.variant & 512) && tj == 0 && lane == 0)
+        for (int k = 1; k < S; ++k) request_tile(k, tr + R * k);
+#endif
       stamp();
 
       // ---- sweep ---------------------------------------------------------------------------
@@ -354,75 +495,114 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
       // 64 or 128 bytes the 8 lanes of a quarter warp then hit 8 different bank groups although the
       // stage is the plain linear image of the rows (which the bulk store needs).
       const int rot = nck > 0 ? ((lane * nck) >> 3) % nck : 0;
-      const bool bulk_ok = kBulk && p.W == wc && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
+      bool bulk_ok = kBulk && p.W == wc && (reinterpret_cast<uintptr_t>(p.out) & 15u) == 0;
+#ifdef GGA_PROFILING
+      if (p.variant & 32) bulk_ok = false;
+#endif
       int buf = 0;
-      auto batch = [&](float4& slot, const int gb) {
-        const float4 pt = slot;
-        if (gb + kDepth * step < bpf) slot = load_pt(gb + kDepth * step);
+      const bool cells_bad = kCells && s_flags[1] != 0;
+      const int n_wide = kCells ? min(s_nwide, kMaxWide) : 0;
+      auto batch = [&](const float4 pt, const int gb) {
         const int bx = bin_of(pt.x, invx, offx), by = bin_of(pt.y, invy, offy);
-        uint32_t* stage = stage_base + (kBulk ? buf * 32 * wcap : 0);
+        uint32_t* stage = stage_base + (kStages == 2 ? buf * 32 * wcap : 0);
         if constexpr (kBulk) {
-          if (bulk_ok) {  // the engine must be done READING this buffer (the store issued two batches ago)
-            if (lane == 0) bulk_wait_read1();
+          if (bulk_ok) {  // the engine must be done READING this buffer
+            if (lane == 0) bulk_wait_read<kStages - 1>();
             __syncwarp();
           }
         }
-
-        // candidate row = maskx[bx] & masky[by], written to the lane's stage row; nz = its non-zero words
-        uint32_t nz = 0u;
         uint32_t* row = stage + lane * wc;
-        if constexpr (kWide) {
+        int best = -1;
+        if constexpr (kCells) {
+          // ---- sparse path: one 8-byte cell entry names the candidates; the row starts empty and the
+          //      boxes that pass the exact test set their bit
+          const uint2 e = *reinterpret_cast<const uint2*>(cells + 2 * (cell_of_bin(by) * kCellsSide + cell_of_bin(bx)));
+          if constexpr (kWide) {
+#pragma unroll
+            for (int j = 0; j < WC / 4; ++j) {
+              int k = j + rot;
+              if (k >= nck) k -= nck;
+              reinterpret_cast<uint4*>(row)[k] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < WC; ++k) row[k] = 0u;
+          }
+          auto test_box = [&](const uint32_t t) {
+            const float4 a = terms[2 * t];
+            if (outside_z(pt.z, a)) return;
+            if (!inside_xy(pt.x, pt.y, a, terms[2 * t + 1])) return;
+            if constexpr (MODE == kModePart) best = best < 0 ? (int)t : min(best, (int)t);
+            else row[t >> 5] |= 1u << (t & 31u);
+          };
+          uint32_t cnt = e.y >> 24;
+#ifdef GGA_PROFILING
+          if (p.variant & 1) cnt = 0u;
+#endif
+          if (cnt > (uint32_t)kCellIds || cells_bad) {
+            // dense spot: every box the axis masks name
+#pragma unroll 1
+            for (int w = 0; w < wc; ++w) {
+              uint32_t m = mx[bx * ms + w] & my[by * ms + w];
+              while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1u;
+                test_box((uint32_t)((w << 5) + j));
+              }
+            }
+          } else {
+            unsigned long long ids = ((unsigned long long)(e.y & 0x00ffffffu) << 32) | e.x;
+#pragma unroll 1
+            for (; cnt != 0u; --cnt) {
+              test_box((uint32_t)(ids & 0xffull));
+              ids >>= 8;
+            }
+#pragma unroll 1
+            for (int i = 0; i < n_wide; ++i) test_box((uint32_t)s_wide[i]);
+          }
+        } else {
+          // ---- general path: candidate row = maskx[bx] & masky[by], written to the lane's stage row
+          //      (nz = its non-zero words); the exact test clears the bits that fail
+          uint32_t nz = 0u;
           const uint4* ax = reinterpret_cast<const uint4*>(mx + bx * ms);
           const uint4* ay = reinterpret_cast<const uint4*>(my + by * ms);
 #pragma unroll
-          for (int j = 0; j < (WC > 0 ? WC / 4 : 8); ++j) {
-            if (WC == 0 && j >= nck) break;
+          for (int j = 0; j < 8; ++j) {
+            if (j >= nck) break;
             int k = j + rot;
             if (k >= nck) k -= nck;
             uint4 a = ax[k];
             const uint4 b = ay[k];
             a.x &= b.x; a.y &= b.y; a.z &= b.z; a.w &= b.w;
-#ifdef GGA_PROFILING
-            if (p.variant & 2) a = make_uint4(0u, 0u, 0u, 0u);
-#endif
             reinterpret_cast<uint4*>(row)[k] = a;
             nz |= ((a.x != 0u ? 1u : 0u) | (a.y != 0u ? 2u : 0u) | (a.z != 0u ? 4u : 0u) | (a.w != 0u ? 8u : 0u)) << (4 * k);
           }
-        } else {
-#pragma unroll
-          for (int k = 0; k < WC; ++k) {
-            const uint32_t a = mx[bx * WC + k] & my[by * WC + k];
-            row[k] = a;
-            nz |= (a != 0u ? 1u : 0u) << k;
-          }
-        }
-
-        // exact test of every candidate, one per loop trip (lanes diverge only in the trip count)
-        int best = -1;
 #ifdef GGA_PROFILING
-        if (p.variant & 1) nz = 0u;
+          if (p.variant & 1) nz = 0u;
 #endif
-        if (nz != 0u) {
-          int w = __ffs(nz) - 1;
-          uint32_t m = row[w], keep = m;
-          for (;;) {
-            const int j = __ffs(m) - 1;
-            m &= m - 1u;
-            const int t = (w << 5) + j;
-            const float4 a = terms[2 * t];
-            bool ok = !outside_z(pt.z, a);
-            if (ok) ok = inside_xy(pt.x, pt.y, a, terms[2 * t + 1]);
-            if constexpr (MODE == kModePart) {
-              if (ok) { best = t0 + t; break; }
-            } else {
-              if (!ok) keep &= ~(1u << j);
-            }
-            if (m == 0u) {
-              if constexpr (MODE != kModePart) row[w] = keep;
-              nz &= nz - 1u;
-              if (nz == 0u) break;
-              w = __ffs(nz) - 1;
-              m = keep = row[w];
+          // one candidate per loop trip (lanes diverge only in the trip count)
+          if (nz != 0u) {
+            int w = __ffs(nz) - 1;
+            uint32_t m = row[w], keep = m;
+            for (;;) {
+              const int j = __ffs(m) - 1;
+              m &= m - 1u;
+              const int t = (w << 5) + j;
+              const float4 a = terms[2 * t];
+              bool ok = !outside_z(pt.z, a);
+              if (ok) ok = inside_xy(pt.x, pt.y, a, terms[2 * t + 1]);
+              if constexpr (MODE == kModePart) {
+                if (ok) { best = t0 + t; break; }
+              } else {
+                if (!ok) keep &= ~(1u << j);
+              }
+              if (m == 0u) {
+                if constexpr (MODE != kModePart) row[w] = keep;
+                nz &= nz - 1u;
+                if (nz == 0u) break;
+                w = __ffs(nz) - 1;
+                m = keep = row[w];
+              }
             }
           }
         }
@@ -490,17 +670,36 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
           __syncwarp();
         }
       };
+
+      int ks = 0;        // ring slot of this warp group's current tile: tr + R * ks
+      uint32_t ph = 0u;  // mbarrier phase of the current pass over the ring
 #pragma unroll 1
-      for (;;) {
-        if (g >= bpf) break;
-        batch(v0, g);
-        g += step;
-        if (g >= bpf) break;
-        batch(v1, g);
-        g += step;
-        if (g >= bpf) break;
-        batch(v2, g);
-        g += step;
+      for (int k = 0;; ++k) {
+        const int ft = rr + rf * (tr + R * k);  // tile of the frame
+        if (ft >= ntiles) break;
+        const int gb = ft * kTileBatches + tj;
+        const int slot = tr + R * ks;
+        if (ft < n_full) {
+          mbar_wait(&s_full[slot], ph);
+          float4 pt;
+          const unsigned char* tile = ring + (size_t)slot * tile_bytes;
+          if constexpr (VEC4) {
+            pt = reinterpret_cast<const float4*>(tile)[tj * 32 + lane];
+          } else {
+            const float* q = reinterpret_cast<const float*>(tile) + (size_t)(tj * 32 + lane) * p.pts_stride;
+            pt = make_float4(q[0], q[1], q[2], 0.f);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[slot]);
+          batch(pt, gb);
+          if (tj == 0 && lane == 0 && rr + rf * (tr + R * (k + S)) < n_full) {
+            mbar_wait(&s_empty[slot], ph);  // the 8 warps of this tile have read their points
+            request_tile(k + S, slot);
+          }
+        } else if (gb < bpf) {
+          batch(load_pt(gb), gb);
+        }
+        if (++ks == S) { ks = 0; ph ^= 1u; }
       }
       if constexpr (kBulk) {
         if (lane == 0) bulk_wait_all();  // the stage buffers are rewritten (or released) next
@@ -541,11 +740,13 @@ struct ProfKnobs {
 ProfKnobs g_prof;
 #endif
 
-size_t sweep_smem_bytes(int mode, int T, int W, int nt) {
+// shared memory of a CTA without the point ring
+size_t sweep_fixed_smem(int mode, int T, int W, int nt) {
   const size_t tcap = T < kChunkBoxes ? T : kChunkBoxes;
   const size_t wcap = W < 32 ? W : 32;
-  const size_t stages = (mode == kModeBits && W >= 4) ? 2 : 1;  // double-buffered when the bulk engine reads them
-  return tcap * 32 + (size_t)2 * kBins * mask_stride((int)wcap) * 4 + (size_t)(nt / 32) * stages * 32 * wcap * 4;
+  const size_t stages = (mode == kModeBits && W >= 4 && W <= 8) ? 2 : 1;  // double-buffered narrow rows (bulk store)
+  const size_t cells = W <= 8 ? (size_t)kCellsSide * kCellsSide * 8 : 0;  // sparse path (<= 256 boxes)
+  return tcap * 32 + (size_t)2 * kBins * mask_stride((int)wcap) * 4 + (size_t)(nt / 32) * stages * 32 * wcap * 4 + cells;
 }
 
 template <int MODE, int WC, int NT, bool VEC4>
@@ -624,8 +825,9 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   sp.trace = g_prof.trace;
   sp.variant = g_prof.variant;
 #endif
-  const size_t smem = sweep_smem_bytes(mode, num_boxes, sp.W, nt);
-  GGA_REQUIRE(smem <= (size_t)gga_max_smem_optin(), "internal: %zu bytes of shared memory requested", smem);
+  const size_t fixed = sweep_fixed_smem(mode, num_boxes, sp.W, nt);
+  const size_t limit = (size_t)gga_max_smem_optin() - 4096;  // minus the kernel's static shared memory (~2.6 KB) and slack
+  GGA_REQUIRE(fixed <= limit, "internal: %zu bytes of shared memory requested", fixed);
   const int nsm = gga_sm_count();
   // CTAs per frame: fill the machine (one CTA per SM) but keep at least one batch per warp; more
   // frames than SMs: one CTA per frame, the CTAs loop over the frames
@@ -637,11 +839,24 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
 #ifdef GGA_PROFILING
   if (g_prof.ranges > 0) rf = g_prof.ranges < sp.bpf ? g_prof.ranges : sp.bpf;
 #endif
-  sp.rf = (int)rf;
   int gy = B;
   if ((long long)gy * rf > nsm) gy = (int)(nsm / rf) > 0 ? (int)(nsm / rf) : 1;
   if (gy > 65535) gy = 65535;
   const dim3 grid((unsigned)rf, (unsigned)gy);
+  // point ring: as many 256-point tiles as a CTA will consume, bounded by the shared memory left;
+  // a multiple of the tiles consumed at a time (one per 8 warps)
+  {
+    const int R = nwarps / kTileBatches;
+    const size_t tile_bytes = (size_t)1024 * pts_stride;
+    const long long ntiles = (sp.bpf + kTileBatches - 1) / kTileBatches;
+    long long want = (ntiles + rf - 1) / rf;  // tiles of one frame per CTA
+    want = (want + R - 1) / R * R;
+    long long fit = (long long)((limit - fixed) / tile_bytes) / R * R;
+    if (fit > kMaxSlots / R * R) fit = kMaxSlots / R * R;
+    sp.ring_slots = (int)(want < fit ? want : fit);
+    if (pts_stride > 16 || sp.ring_slots < R) sp.ring_slots = 0;
+  }
+  const size_t smem = fixed + (size_t)sp.ring_slots * 1024 * pts_stride;
   const bool vec4 = pts_stride == 4 && (reinterpret_cast<uintptr_t>(points) & 15) == 0;
   if (mode == kModeBits) return launch_mode<kModeBits>(sp, nt, vec4, grid, smem, st);
   if (mode == kModeAll) return launch_mode<kModeAll>(sp, nt, vec4, grid, smem, st);

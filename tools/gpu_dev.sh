@@ -20,6 +20,6 @@ $Q --cfg 2 --mode part
 $Q --cfg 2 --mode all
 export GGA_B200_LIB=$PWD/gga_b200/_C/libgga_b200_prof.so
 $Q --cfg 2 --nt 1024 --variant 0 --trace
-$Q --cfg 2 --nt 1024 --variant 1,3,8,9,11
+$Q --cfg 2 --nt 1024 --variant 1,8,9
 } > gpurun_out/${TAG}_qb.log 2>&1
 cat gpurun_out/${TAG}_qb.log

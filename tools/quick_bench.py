@@ -15,9 +15,28 @@ import gga_b200 as G  # noqa: E402
 from gga_b200 import synth  # noqa: E402
 
 
+def sm_clock():
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        return int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception:
+        return -1
+
+
+SPIN_S = 0.0
+
+
 def time_ms(fn, iters=20, warm=3):
+    import time
     for _ in range(warm):
         fn()
+    t0 = time.time()
+    while time.time() - t0 < SPIN_S:      # keep the GPU busy so that the SM clock has ramped up
+        for _ in range(50):
+            fn()
+        torch.cuda.synchronize()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
@@ -40,7 +59,10 @@ def main():
     ap.add_argument('--ranges', default='0')
     ap.add_argument('--variant', default='0')
     ap.add_argument('--trace', action='store_true')
+    ap.add_argument('--spin', type=float, default=0.0)
     a = ap.parse_args()
+    global SPIN_S
+    SPIN_S = a.spin
     c = synth.CONFIGS[a.cfg]
     F = a.frames or c['frames_per_gpu']
     N, M = a.N or c['N'], a.M or c['M']
@@ -80,8 +102,9 @@ def main():
                 for k in range(pool):
                     call(k)
             ms = time_ms(g_.replay) / pool
+            clk = sm_clock()
             r = dict(cfg=a.cfg, mode=a.mode, F=F, N=N, M=M, nt=nt, ranges=rg, variant=var, us=round(ms * 1e3, 2),
-                     gbs=round(bytes_step / ms / 1e6, 1), frac=round(bytes_step / ms / 1e6 / 6537.6, 3), pool=pool,
+                     gbs=round(bytes_step / ms / 1e6, 1), frac=round(bytes_step / ms / 1e6 / 6537.6, 3), pool=pool, sm_mhz_after=clk,
                      sorted=not a.unsorted)
             print(json.dumps(r), flush=True)
             if a.trace and prof:
@@ -101,8 +124,8 @@ def main():
                 t0 = t[:, :, 0].min()
                 rel = (t - t0) / 1e3
                 nbw = (min(M, 1024) + 31) // 32
-                names = ['past wait', 'loads issued', 'B1 | terms start', 'fill | terms done', 'index done', 'sweep done']
-                for cls, sel in (('box warps', slice(0, nbw)), ('terms warps', slice(nbw, 2 * nbw)), ('other warps', slice(2 * nbw, nw))):
+                names = ['past wait', 'boxes requested', 'B1', 'rects published', 'cells filled', 'tables done', 'index done', 'sweep done']
+                for cls, sel in (('box warps', slice(0, nbw)),):
                     sub = rel[:, sel, :]
                     if sub.size == 0:
                         continue
