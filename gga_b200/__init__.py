@@ -3,7 +3,7 @@ membership masking, 3D-box -> 2D-box projection, IoU/GIoU/L1 consistency loss + 
 pseudo-label matching.  Host side mirrors the reference's function / loss-module API; the
 compute is hand-written CUDA behind the C ABI of include/gga_b200.h.  No CPU fallback."""
 from . import _lib
-from .ops import (points_in_boxes_all, points_in_boxes_bits, points_in_boxes_cpu, points_in_boxes_part,
+from .ops import (hit_list, points_in_boxes_all, points_in_boxes_bits, points_in_boxes_cpu, points_in_boxes_part,
                   row_words, unpack_bits)
 from .project import box3d_project, pad_proj
 from .losses import (AxisAlignedIoULoss, GIoULoss, IoULoss, L1Loss, ProjectedGIoULoss, ProjectedIoULoss,

@@ -63,6 +63,7 @@ SIGNATURES = {
     'gga_points_in_boxes_all': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     'gga_points_in_boxes_part': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p], c_int),
     'gga_points_in_boxes_all_host': ([c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int], c_int),
+    'gga_pib_hit_list': ([c_void_p, ctypes.c_int64, c_int, ctypes.c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p], c_int),
     'gga_box_project_loss': ([ctypes.POINTER(BoxLossArgs), c_void_p], c_int),
     'gga_box_project_backward': ([c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, ctypes.c_float, c_void_p], c_int),
@@ -85,6 +86,9 @@ SIGNATURES = {
     'gga_step_create': ([c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     'gga_step_destroy': ([c_void_p], c_int),
     'gga_step_device_bits': ([c_void_p, ctypes.POINTER(c_void_p)], c_int),
+    'gga_step_run_host_hits': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),
     'gga_step_run_host': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                            ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                            c_void_p, c_void_p, c_void_p], c_int),

@@ -710,6 +710,46 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
   }
 }
 
+// Compacts bit-packed rows into a list of (point, box) pairs: one warp per 32 rows, the pairs of a
+// warp are appended with one atomicAdd (the order of the list is unspecified; the count is exact even
+// when the list overflows its capacity, pairs beyond it are dropped).
+__global__ void __launch_bounds__(256) hit_list_kernel(const uint32_t* __restrict__ bits, long long rows, int W,
+                                                       long long row_base, int32_t* __restrict__ pairs, int capacity,
+                                                       int32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  for (long long r0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 32; r0 < rows; r0 += (long long)gridDim.x * 256) {
+    const long long r = r0 + lane;
+    int n = 0;
+    if (r < rows)
+      for (int w = 0; w < W; ++w) n += __popc(__ldg(bits + r * W + w));
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) continue;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n;
+    if (n) {
+      for (int w = 0; w < W; ++w) {
+        uint32_t m = __ldg(bits + r * W + w);
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1u;
+          if (base < capacity) {
+            pairs[2 * (long long)base] = (int32_t)(row_base + r);
+            pairs[2 * (long long)base + 1] = (w << 5) + j;
+          }
+          ++base;
+        }
+      }
+    }
+  }
+}
+
 __global__ void sincos_test_kernel(const float* __restrict__ x, long long n, float* sn, float* cs) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -920,6 +960,23 @@ extern "C" int gga_points_in_boxes_all_host(const float* points, int pts_stride,
     gga_set_error("points_in_boxes_all_host: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
     return GGA_ERR_CUDA;
   }
+  return GGA_OK;
+}
+
+extern "C" int gga_pib_hit_list(const uint32_t* bits, int64_t num_rows, int num_boxes, int64_t row_base,
+                                int32_t* pairs, int capacity, int32_t* count, int reset_count, void* stream) {
+  GGA_REQUIRE(num_rows >= 0 && num_boxes >= 0 && capacity >= 0, "negative size");
+  GGA_REQUIRE(count != nullptr, "null count pointer");
+  cudaStream_t st = gga_stream(stream);
+  if (reset_count) GGA_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+  if (num_rows == 0 || num_boxes == 0) return GGA_OK;
+  GGA_REQUIRE(bits != nullptr && (pairs != nullptr || capacity == 0), "null pointer");
+  const int W = gga_pib_row_words(num_boxes);
+  long long blocks = (num_rows + 255) / 256;
+  const long long cap_blocks = (long long)gga_sm_count() * 8;
+  if (blocks > cap_blocks) blocks = cap_blocks;
+  hit_list_kernel<<<(unsigned)blocks, 256, 0, st>>>(bits, num_rows, W, row_base, pairs, capacity, count);
+  GGA_CHECK_CUDA(cudaGetLastError());
   return GGA_OK;
 }
 

@@ -32,6 +32,9 @@ struct StepCtx {
   float* d_grad;      // [F*M, 7]
   void* d_scratch;    // loss-reduction scratch of this context (zeroed at creation)
   size_t scratch_bytes;
+  int32_t* d_pairs;   // [pair_capacity, 2] hit list of the masks (allocated on first use)
+  int32_t* d_count;   // [1]
+  int pair_capacity;
   cudaStream_t streams[kMaxStreams];
   cudaStream_t box_stream;
   cudaEvent_t boxes_ready, done[kMaxStreams], box_done;
@@ -42,6 +45,8 @@ void destroy(StepCtx* c) {
   cudaFree(c->d_points); cudaFree(c->d_boxes); cudaFree(c->d_proj); cudaFree(c->d_target); cudaFree(c->d_weight);
   cudaFree(c->d_bits); cudaFree(c->d_box2d); cudaFree(c->d_loss); cudaFree(c->d_loss_sum); cudaFree(c->d_grad);
   cudaFree(c->d_scratch);
+  if (c->d_pairs) cudaFree(c->d_pairs);
+  if (c->d_count) cudaFree(c->d_count);
   for (int i = 0; i < kMaxStreams; ++i) {
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->done[i]) cudaEventDestroy(c->done[i]);
@@ -106,9 +111,10 @@ extern "C" int gga_step_destroy(void* ctx) {
 // Enqueues the whole step; returns on the first failure WITHOUT synchronising (the caller does).
 static int enqueue_step(StepCtx* c, const float* points, const float* boxes, const float* lidar2img,
                         const float* target, const float* weight, int proj_mode, int loss_kind, float loss_weight,
-                        float avg_factor, float eps, float depth_clamp, uint32_t* bits, float* loss_sum,
+                        float avg_factor, float eps, float depth_clamp, uint32_t* bits, bool hits, float* loss_sum,
                         float* grad_boxes) {
   const size_t F = c->F, N = c->N, M = c->M, st = c->pts_stride, W = c->W;
+  if (hits) GGA_CHECK_CUDA(cudaMemsetAsync(c->d_count, 0, sizeof(int32_t), c->box_stream));
   // boxes first: every frame's membership needs them
   GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_boxes, boxes, F * M * 7 * sizeof(float), cudaMemcpyHostToDevice, c->box_stream));
   GGA_CHECK_CUDA(cudaEventRecord(c->boxes_ready, c->box_stream));
@@ -125,6 +131,12 @@ static int enqueue_step(StepCtx* c, const float* points, const float* boxes, con
     if (bits)
       GGA_CHECK_CUDA(cudaMemcpyAsync(bits + f * N * W, c->d_bits + f * N * W, N * W * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, q));
+    if (hits) {
+      const int rc2 = gga_pib_hit_list(c->d_bits + f * N * W, (int64_t)N, (int)M, (int64_t)(f * N), c->d_pairs,
+                                       c->pair_capacity, c->d_count, 0, q);
+      if (rc2 != GGA_OK) return rc2;
+    }
+    GGA_CHECK_CUDA(cudaEventRecord(c->done[s], q));
   }
   // projection + loss forward / backward
   cudaStream_t b = c->box_stream;
@@ -158,7 +170,7 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
   GGA_CHECK_CUDA(cudaGetDevice(&dev));
   GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
   const int rc = enqueue_step(c, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight,
-                              avg_factor, eps, depth_clamp, bits, loss_sum, grad_boxes);
+                              avg_factor, eps, depth_clamp, bits, false, loss_sum, grad_boxes);
   // The call is synchronous, like the CPU op it stands in for — and on a failure half-way the
   // copies already enqueued still reference the caller's host buffers: drain every stream first.
   cudaError_t e = cudaStreamSynchronize(c->box_stream);
@@ -170,6 +182,57 @@ extern "C" int gga_step_run_host(void* ctx, const float* points, const float* bo
   if (e != cudaSuccess) {
     gga_set_error("gga_step_run_host: %s", cudaGetErrorString(e));
     return GGA_ERR_CUDA;
+  }
+  return GGA_OK;
+}
+
+extern "C" int gga_step_run_host_hits(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                                      const float* target, const float* weight, int proj_mode, int loss_kind,
+                                      float loss_weight, float avg_factor, float eps, float depth_clamp,
+                                      int32_t* hits, int hit_capacity, int32_t* n_hits, float* loss_sum,
+                                      float* grad_boxes) {
+  StepCtx* c = static_cast<StepCtx*>(ctx);
+  GGA_REQUIRE(c != nullptr, "null context");
+  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes && hits && n_hits, "null host pointer");
+  GGA_REQUIRE(avg_factor > 0.f && hit_capacity > 0, "avg_factor and hit_capacity must be positive");
+  int dev = 0;
+  GGA_CHECK_CUDA(cudaGetDevice(&dev));
+  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
+  if (c->pair_capacity < hit_capacity) {  // (re)allocated outside the pipeline, first use only
+    GGA_CHECK_CUDA(cudaDeviceSynchronize());
+    if (c->d_pairs) cudaFree(c->d_pairs);
+    c->d_pairs = nullptr;
+    c->pair_capacity = 0;
+    GGA_CHECK_CUDA(cudaMalloc(&c->d_pairs, (size_t)hit_capacity * 2 * sizeof(int32_t)));
+    if (!c->d_count) GGA_CHECK_CUDA(cudaMalloc(&c->d_count, sizeof(int32_t)));
+    c->pair_capacity = hit_capacity;
+  }
+  int rc = enqueue_step(c, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight, avg_factor,
+                        eps, depth_clamp, nullptr, true, loss_sum, grad_boxes);
+  cudaError_t e = cudaSuccess;
+  if (rc == GGA_OK) {  // the count first (all frame streams joined), then exactly that many pairs
+    cudaStream_t b = c->box_stream;
+    for (int s = 0; s < c->n_streams && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(b, c->done[s], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_hits, c->d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, b);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b);
+    if (e == cudaSuccess) {
+      const int n = *n_hits < hit_capacity ? *n_hits : hit_capacity;
+      if (n > 0) e = cudaMemcpyAsync(hits, c->d_pairs, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, b);
+    }
+  }
+  cudaError_t e1 = cudaStreamSynchronize(c->box_stream);
+  for (int s = 0; s < c->n_streams; ++s) {
+    const cudaError_t es = cudaStreamSynchronize(c->streams[s]);
+    if (e1 == cudaSuccess) e1 = es;
+  }
+  if (rc != GGA_OK) return rc;
+  if (e != cudaSuccess || e1 != cudaSuccess) {
+    gga_set_error("gga_step_run_host_hits: %s", cudaGetErrorString(e != cudaSuccess ? e : e1));
+    return GGA_ERR_CUDA;
+  }
+  if (*n_hits > hit_capacity) {
+    gga_set_error("hit list overflow: %d pairs, capacity %d", *n_hits, hit_capacity);
+    return GGA_ERR_UNSUPPORTED;
   }
   return GGA_OK;
 }

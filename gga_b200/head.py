@@ -74,12 +74,25 @@ def boundary_projection_loss(pred_iou, target_box, mask, boundary_mask, code_wei
 # ----------------------------------------------------------------------------------------------
 # Point-to-Box Alignment (PAL): centerpoint_head_gga.py:184-248 (distances), :690-699 (losses)
 # ----------------------------------------------------------------------------------------------
-def pack_in_box_points(ibp_points, device):
+def pack_in_box_points(ibp_points, device, max_objs=None):
     """``GGA_in_box_points`` — per frame a list (one entry per object) of ``[n_i, >=2]`` tensors
     (float64 ``(x, y, z, 1)`` in the reference, kitti_converter_gga.py:245-247) — packed ONCE
     into the CSR layout the kernel reads: (points_xy float32 [P, 2], offsets int32 [n_obj + 1],
     max_points int), objects in frame-major order.  The reference moves every list entry to the device
-    separately (:469-470) and uses only ``[:, :2].float()`` (:201)."""
+    separately (:469-470) and uses only ``[:, :2].float()`` (:201).
+
+    ``max_objs`` = K of the head's ``[B, K, 5]`` boxes: the lists are RAGGED in the reference (a frame
+    has n_obj <= max_objs clusters, centerpoint_head_gga.py:463-479,693) and the rows of the missing
+    objects stay zero (:190-199); every frame is padded here to ``max_objs`` entries with empty objects
+    so that object ``b * K + k`` of the packed layout is row ``[b, k]``."""
+    if max_objs is not None:
+        empty = torch.zeros((0, 2), dtype=torch.float32)
+        padded = []
+        for frame in ibp_points:
+            frame = list(frame)
+            assert len(frame) <= max_objs, f'{len(frame)} point clusters in a frame, but only {max_objs} objects'
+            padded.append(frame + [empty] * (max_objs - len(frame)))
+        ibp_points = padded
     flat = [t for frame in ibp_points for t in frame]
     counts = torch.tensor([0] + [int(t.shape[0]) for t in flat], dtype=torch.int64)
     offsets = torch.cumsum(counts, 0).to(torch.int32)
@@ -135,10 +148,12 @@ def get_distance_bev(ibp_points, pred_box_bev, packed=None):
     """Same signature and return layout as ``CenterHead_GGA.get_distance_bev``
     (centerpoint_head_gga.py:241-248): ``ibp_points`` = per-frame lists of per-object point
     tensors, ``pred_box_bev [B, K, 5]``; returns ``(pts_min_dis, pts_x_dis, pts_y_dis)``, each
-    ``[B, K, 1]``.  Pass ``packed=pack_in_box_points(...)`` to skip the per-call packing."""
+    ``[B, K, 1]``; a frame may list fewer than K clusters (the rows of the others are zero, like
+    the reference's ``new_zeros`` rows).  Pass ``packed=pack_in_box_points(..., max_objs=K)`` to skip
+    the per-call packing."""
     b, k, _ = pred_box_bev.shape
-    xy, off, mx = packed if packed is not None else pack_in_box_points(ibp_points, pred_box_bev.device)
-    assert off.numel() == b * k + 1, f'expected {b * k} objects, got {off.numel() - 1}'
+    xy, off, mx = packed if packed is not None else pack_in_box_points(ibp_points, pred_box_bev.device, max_objs=k)
+    assert off.numel() == b * k + 1, f'expected {b * k} objects, got {off.numel() - 1} (pack with max_objs=K)'
     d = point_box_distances(xy, off, pred_box_bev.reshape(-1, 5), mx).reshape(b, k, 3)
     return d[..., 0:1], d[..., 1:2], d[..., 2:3]
 

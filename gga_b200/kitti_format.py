@@ -43,13 +43,35 @@ def _empty_anno():
             'rotation_y': np.array([]), 'score': np.array([])}
 
 
-def bbox2result_kitti(net_outputs, data_infos, class_names, pcd_limit_range, pklfile_prefix=None,
-                      submission_prefix=None, device=None):
-    """Same arguments as the reference method (``self.data_infos`` / ``self.pcd_limit_range``
-    passed explicitly).  ``net_outputs[i]`` = dict(boxes_3d = LiDAR boxes (an object with
-    ``.tensor`` or a [n, 7] tensor, bottom centre), scores_3d [n], labels_3d [n]).
-    Returns ``list[dict]`` in KITTI format; writes ``{submission_prefix}/{idx:06d}.txt`` and
-    ``{pklfile_prefix}.pkl`` when asked."""
+REFERENCE_DUMP_PATH = './data/kitti_pesudo/kitti_infos_trainval_GGA_pseudo.pkl'   # utils_pseudo_labels_gga.py:69
+
+
+class KittiResultFormatter:
+    """Carries what the reference method reads from ``self`` (``self.data_infos``,
+    ``self.pcd_limit_range``) so that :meth:`bbox2result_kitti` has the reference's exact signature
+    (``kitti_dataset_GGA_match.py:458-462``); a dataset object can equally be passed to
+    :func:`bbox2result_kitti` through ``dataset=``."""
+
+    def __init__(self, data_infos, pcd_limit_range, device=None):
+        self.data_infos, self.pcd_limit_range, self.device = data_infos, pcd_limit_range, device
+
+    def bbox2result_kitti(self, net_outputs, class_names, pklfile_prefix=None, submission_prefix=None):
+        return bbox2result_kitti(net_outputs, class_names, pklfile_prefix, submission_prefix, dataset=self,
+                                 device=self.device)
+
+
+def bbox2result_kitti(net_outputs, class_names, pklfile_prefix=None, submission_prefix=None, *, dataset=None,
+                      data_infos=None, pcd_limit_range=None, device=None):
+    """The reference method's arguments in its order (``net_outputs, class_names, pklfile_prefix,
+    submission_prefix``); what it reads from ``self`` comes keyword-only: ``dataset`` (any object with
+    ``data_infos`` and ``pcd_limit_range``, e.g. the reference's dataset) or the two values themselves.
+    ``net_outputs[i]`` = dict(boxes_3d = LiDAR boxes (an object with ``.tensor`` or a [n, 7] tensor,
+    bottom centre), scores_3d [n], labels_3d [n]).  Returns ``list[dict]`` in KITTI format; writes
+    ``{submission_prefix}/{idx:06d}.txt`` and ``{pklfile_prefix}.pkl`` when asked."""
+    if dataset is not None:
+        data_infos, pcd_limit_range = dataset.data_infos, dataset.pcd_limit_range
+    assert data_infos is not None and pcd_limit_range is not None, 'pass dataset= or data_infos= and pcd_limit_range='
+
     assert len(net_outputs) == len(data_infos), 'invalid list length of network outputs'
     dev = torch.device(device if device is not None else 'cuda')
     assert dev.type == 'cuda', 'bbox2result_kitti runs the projection on a CUDA device (there is no CPU path)'
@@ -138,14 +160,20 @@ def _strip_dontcare(anno, keys=None):
             anno[key] = anno[key][select]
 
 
-def pseudo_label_matching_kitti(gt_infos, dt_annos, out_path=None, device=None):
-    """``pseudo_label_matching_kitti`` (``tools/utils_pseudo_labels_gga.py:17-88``).
+def pseudo_label_matching_kitti(gt_infos, dt_annos, metric=0, num_parts=200, *, out_path=REFERENCE_DUMP_PATH,
+                                device=None, return_infos=False):
+    """``pseudo_label_matching_kitti(gt_infos, dt_annos, metric=0, num_parts=200) -> gt_annos``
+    (``tools/utils_pseudo_labels_gga.py:17-84``), same positional signature and return value.
 
     Modifies ``gt_infos[i]['annos']`` in place exactly like the reference (pops
-    ``GGA_in_box_points``, removes DontCare / unused classes) and returns ``(gt_annos, new_infos)``:
-    the cleaned annotations (the reference's return value) and the deep-copied infos whose
-    ``annos`` are rewritten from the matched detections (what the reference dumps to
-    ``kitti_infos_trainval_GGA_pseudo.pkl``; written to ``out_path`` when given)."""
+    ``GGA_in_box_points``, removes DontCare / unused classes), rewrites the annotations of a deep
+    copy of the infos from the matched detections and dumps that copy to ``out_path`` (default: the
+    reference's fixed file, its directory created if needed; ``None`` = no file).  Returns the
+    cleaned ``gt_annos`` like the reference; ``return_infos=True`` returns ``(gt_annos, new_infos)``.
+    ``metric`` must be 0 (2D image boxes, the only one the GGA tool uses, ``:45``); ``num_parts`` only
+    chunks the reference's IoU computation and has no effect on the result."""
+    if metric != 0:
+        raise NotImplementedError('pseudo-label matching uses the 2D image-box IoU (metric=0)')
     gt_annos = [info['annos'] for info in gt_infos]
     assert len(gt_annos) == len(dt_annos)
     new_infos = copy.deepcopy(gt_infos)
@@ -180,6 +208,9 @@ def pseudo_label_matching_kitti(gt_infos, dt_annos, out_path=None, device=None):
         sample.pop('annos')
         sample['annos'] = new_annos[f]
     if out_path is not None:
+        d = os.path.dirname(out_path)
+        if d:
+            os.makedirs(d, exist_ok=True)
         with open(out_path, 'wb') as fh:
             pickle.dump(new_infos, fh)
-    return gt_annos, new_infos
+    return (gt_annos, new_infos) if return_infos else gt_annos

@@ -75,6 +75,35 @@ def points_in_boxes_bits(points, boxes):
     return out
 
 
+def hit_list(bits, num_boxes, capacity=None):
+    """(row, box) pairs of the set bits of bit-packed rows.
+
+    Args:
+        bits (Tensor): int32 [..., W] as returned by ``points_in_boxes_bits`` (rows are numbered in
+            memory order over the leading dimensions, e.g. ``frame * M + point``).
+        num_boxes (int): T.
+        capacity (int): pairs to make room for (default: 4 per row, at least 1024).
+    Returns:
+        Tensor: int32 [n_hits, 2] = (row, box); the order is unspecified.  Synchronises once (the
+        count is read back); raises if the list did not fit ``capacity``.
+    """
+    assert bits.is_cuda and bits.dtype == torch.int32 and bits.is_contiguous()
+    L = _lib.load()
+    W = bits.shape[-1]
+    assert W == L.gga_pib_row_words(int(num_boxes)), 'row width does not match num_boxes'
+    rows = bits.numel() // max(W, 1)
+    cap = int(capacity) if capacity is not None else max(1024, 4 * rows)
+    pairs = torch.empty((cap, 2), dtype=torch.int32, device=bits.device)
+    count = torch.empty((1,), dtype=torch.int32, device=bits.device)
+    with torch.cuda.device(bits.device):
+        _lib.check(L.gga_pib_hit_list(bits.data_ptr(), rows, int(num_boxes), 0, pairs.data_ptr(), cap, count.data_ptr(),
+                                      1, _lib.current_stream(bits.device)), 'pib_hit_list')
+    n = int(count.item())
+    if n > cap:
+        raise RuntimeError(f'hit list overflow: {n} pairs, capacity {cap}')
+    return pairs[:n]
+
+
 def row_words(num_boxes):
     return _lib.load().gga_pib_row_words(int(num_boxes))
 

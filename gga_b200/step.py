@@ -123,6 +123,8 @@ class GeometryStep:
     def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3, masks_to_host=True):
         """Same step with HOST inputs (page-locked torch CPU tensors) and HOST results: returns
         (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous.
+        ``masks_to_host='hits'`` returns them as int32 [n_hits, 2] = (frame * N + point, box) pairs
+        (order unspecified) instead of dense rows: ~25x fewer bytes over PCIe at KITTI densities.
         ``masks_to_host=False`` leaves the masks on the device (the training use: the head consumes
         them there) and returns a CUDA int32 tensor view of the library's buffer instead — valid
         until the next ``run_host`` / ``close``.
@@ -147,6 +149,8 @@ class GeometryStep:
         for t in (points, boxes, lidar2img, target, weight):
             assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()), \
                 'run_host takes contiguous fp32 CPU tensors'
+        if masks_to_host == 'hits':
+            return self._run_host_hits(h, points, boxes, lidar2img, target, weight, avg_factor)
         n = self.F * self.M
         with torch.cuda.device(self.device):
             _lib.check(L.gga_step_run_host(
@@ -158,6 +162,23 @@ class GeometryStep:
         if not masks_to_host:
             return self._device_bits(), float(h['h_loss'][0]), h['h_grad']
         return h['h_bits'], float(h['h_loss'][0]), h['h_grad']
+
+    def _run_host_hits(self, h, points, boxes, lidar2img, target, weight, avg_factor):
+        L = self.L
+        if 'h_hits' not in h:
+            cap = max(4096, 2 * self.F * self.N)
+            h['h_hits'] = torch.empty((cap, 2), dtype=torch.int32).pin_memory()
+            h['h_nhits'] = torch.zeros((1,), dtype=torch.int32).pin_memory()
+        n = self.F * self.M
+        with torch.cuda.device(self.device):
+            _lib.check(L.gga_step_run_host_hits(
+                h['ctx'], points.data_ptr(), boxes.data_ptr(), lidar2img.data_ptr(), target.data_ptr(),
+                None if weight is None else weight.data_ptr(), self.mode, self.kind, self.loss_weight,
+                float(avg_factor if avg_factor is not None else max(n, 1)), self.eps, self.depth_clamp,
+                h['h_hits'].data_ptr(), h['h_hits'].shape[0], h['h_nhits'].data_ptr(), h['h_loss'].data_ptr(),
+                h['h_grad'].data_ptr()), 'step_run_host_hits')
+        self.last_hits = int(h['h_nhits'][0])
+        return h['h_hits'][:self.last_hits], float(h['h_loss'][0]), h['h_grad']
 
     def _device_bits(self):
         h = self._host
@@ -187,5 +208,9 @@ class GeometryStep:
     def host_bytes(self, points, boxes, lidar2img, target, weight, masks_to_host=True):
         """(h2d, d2h) bytes moved by one ``run_host``."""
         h2d = sum(t.numel() * t.element_size() for t in (points, boxes, lidar2img, target, weight))
-        d2h = (self.bits.numel() * 4 if masks_to_host else 0) + self.grad_boxes.numel() * 4 + 4
+        if masks_to_host == 'hits':   # (row, box) pairs of the last run + their count
+            mask_bytes = 8 * getattr(self, 'last_hits', 0) + 4
+        else:
+            mask_bytes = self.bits.numel() * 4 if masks_to_host else 0
+        d2h = mask_bytes + self.grad_boxes.numel() * 4 + 4
         return h2d, d2h

@@ -264,6 +264,19 @@ def main():
     hd['gps_rot'], hd['gps_ratio'], hd['gps_iou'], hd['gps_bev'] = (rot.detach().numpy(), ratio.detach().numpy(),
                                                                      piou.detach().numpy(), pbev.detach().numpy())
     hd['gps_gi'], hd['gps_gb'], hd['gps_gr'], hd['gps_grad_pred'] = gi.numpy(), gb.numpy(), gr.numpy(), tp.grad.numpy()
+    # the same reference source text evaluated in float64 (same inputs, .double()): the yardstick the
+    # 1e-5 parity tests hold the CUDA kernels to (tests/parity.py); consumes no random numbers
+    try:
+        tp64 = torch.from_numpy(pred).double().requires_grad_(True)
+        rot64, _ = H.GGA_calculate_rotation(tp64[..., 6:])
+        ratio64, piou64, pbev64 = H.get_prediction_single(tp64, torch.from_numpy(ind), torch.from_numpy(l2i_all).double(), rot64)
+        assert piou64.dtype == torch.float64
+        ((piou64 * gi.double()).sum() + (pbev64 * gb.double()).sum() + (ratio64 * gr.double()).sum()).backward()
+        hd['gps_iou_f64'], hd['gps_bev_f64'], hd['gps_ratio_f64'] = (piou64.detach().numpy(), pbev64.detach().numpy(),
+                                                                     ratio64.detach().numpy())
+        hd['gps_grad_pred_f64'] = tp64.grad.numpy()
+    except Exception as e:  # noqa: BLE001
+        print('get_prediction_single does not run in float64:', repr(e))
     # Point-to-Box Alignment: ragged in-box point lists (float64 [n_i, 4] = x, y, z, 1 like
     # kitti_converter_gga.py:245-247), some empty, some far outside the predicted box
     bev = pbev.detach().clone().requires_grad_(True)

@@ -144,6 +144,20 @@ def load_reference(points_in_boxes_all=None, points_in_boxes_part=None):
     return ns
 
 
+def expose_for_reference_tests():
+    """Completes the module tree so that the reference's own test files
+    (tests/test_utils/test_box3d.py, ...) can be imported: `mmdet3d.core.bbox.transforms`
+    (bbox3d2roi, bbox3d_mapping_back; transforms.py needs only torch) and the public names the
+    tests import from `mmdet3d.core.bbox` / `mmdet3d.core.bbox.structures.utils`."""
+    load_reference()
+    tr = _load('mmdet3d.core.bbox.transforms', 'mmdet3d/core/bbox/transforms.py')
+    core_bbox = sys.modules['mmdet3d.core.bbox']
+    for k in ('bbox3d2roi', 'bbox3d_mapping_back', 'bbox3d2result'):
+        if hasattr(tr, k):
+            setattr(core_bbox, k, getattr(tr, k))
+    return core_bbox
+
+
 def load_head_functions(train_cfg, norm_bbox=True):
     """The GGA head methods of the reference, extracted from its source file and bound to a
     stand-in ``self`` (the module itself cannot be imported: its header needs mmcv.cnn and the

@@ -16,12 +16,12 @@ def pytest_configure(config):
 def pytest_collection_modifyitems(config, items):
     import torch
     has_gpu = torch.cuda.is_available()
-    has_ref = os.path.isdir('/root/reference/mmdet3d')
+    has_ref = os.path.isdir(os.path.join(os.environ.get('GGA_REFERENCE_ROOT', '/root/reference'), 'mmdet3d'))
     for it in items:
         if 'gpu' in it.keywords and not has_gpu:
             it.add_marker(pytest.mark.skip(reason='no CUDA device'))
         if 'refonly' in it.keywords and not has_ref:
-            it.add_marker(pytest.mark.skip(reason='/root/reference not present'))
+            it.add_marker(pytest.mark.skip(reason='reference tree not present (GGA_REFERENCE_ROOT)'))
 
 
 @pytest.fixture(scope='session')

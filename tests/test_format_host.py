@@ -40,7 +40,8 @@ def numpy_matcher(dt, do, gt, go, return_overlaps=False):
 def test_annos_rewrite_equals_reference(monkeypatch):
     monkeypatch.setattr(KF, 'match_dt_to_gt', numpy_matcher)
     infos, _ = synth.make_detection_frames(2024, FORMAT_COUNTS)
-    cleaned, new_infos = KF.pseudo_label_matching_kitti(copy.deepcopy(infos), golden_annos(), device='cpu')
+    cleaned, new_infos = KF.pseudo_label_matching_kitti(copy.deepcopy(infos), golden_annos(), 0, 200, out_path=None, device='cpu',
+                                                        return_infos=True)
     for f in range(len(infos)):
         ref_keys = [k[len(f'f{f}_new_'):] for k in GOLD.files if k.startswith(f'f{f}_new_')]
         assert list(new_infos[f]['annos'].keys()) == ref_keys
@@ -57,7 +58,8 @@ def test_bbox2result_kitti_needs_the_gpu():
     infos, dets = synth.make_detection_frames(1, (3,))
     if not torch.cuda.is_available():
         try:
-            KF.bbox2result_kitti(dets, infos, ['Pedestrian', 'Cyclist', 'Car'], list(synth.KITTI_MATCH_RANGE), device='cpu')
+            KF.bbox2result_kitti(dets, ['Pedestrian', 'Cyclist', 'Car'], data_infos=infos,
+                                 pcd_limit_range=list(synth.KITTI_MATCH_RANGE), device='cpu')
         except AssertionError as e:
             assert 'no CPU path' in str(e)
         else:

@@ -9,7 +9,9 @@ import pytest
 import torch
 
 import gga_b200 as G
+from oracle import geometry as og
 from oracle import losses as ol
+from parity import close64, d64
 
 pytestmark = pytest.mark.gpu
 CFG = dict(grid_size=[1408, 1600, 40], out_size_factor=8, voxel_size=[0.05, 0.05, 0.1],
@@ -32,8 +34,11 @@ def test_get_prediction_single_vs_reference_golden(H):
     assert np.allclose(iou.detach().cpu().numpy(), H['gps_iou'], rtol=1e-5, atol=2e-3)
     ((iou * torch.from_numpy(H['gps_gi']).cuda()).sum() + (bev * torch.from_numpy(H['gps_gb']).cuda()).sum() +
      (ratio * torch.from_numpy(H['gps_gr']).cuda()).sum()).backward()
-    g, rg = pred.grad.cpu().numpy(), H['gps_grad_pred']
-    assert np.allclose(g, rg, rtol=1e-4, atol=1e-4 * np.abs(rg).max())
+    # float64 yardstick: the reference's OWN source text (centerpoint_head_gga.py:250-341) evaluated on the
+    # same inputs in double (oracle/gen_golden.py -> gps_*_f64)
+    assert close64(iou, H['gps_iou_f64'], H['gps_iou'], what='get_prediction_single box2d')
+    assert close64(bev, H['gps_bev_f64'], H['gps_bev'], what='get_prediction_single bev')
+    assert close64(pred.grad, H['gps_grad_pred_f64'], H['gps_grad_pred'], what='get_prediction_single grad')
 
 
 def _lists(H, device):
@@ -55,8 +60,38 @@ def test_point_box_alignment_vs_reference_golden(H):
         assert np.allclose(got.detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(ref).max())), key
     ((dmin * torch.from_numpy(H['pal_cm']).cuda()).sum() + (dx * torch.from_numpy(H['pal_cx']).cuda()).sum() +
      (dy * torch.from_numpy(H['pal_cy']).cuda()).sum()).backward()
-    g, rg = bev.grad.cpu().numpy(), H['pal_grad_bev']
-    assert np.allclose(g, rg, rtol=1e-4, atol=1e-5 * np.abs(rg).max())
+    counts = H['pal_counts']
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    b64 = d64(torch.from_numpy(H['pal_bev']).reshape(-1, 5).requires_grad_(True))
+    m64, x64, y64 = ol.point_box_distances(d64(H['pal_points_xy']), off, b64)
+    shp = H['pal_min'].shape
+    ((m64.reshape(shp) * d64(H['pal_cm'])).sum() + (x64.reshape(shp) * d64(H['pal_cx'])).sum() +
+     (y64.reshape(shp) * d64(H['pal_cy'])).sum()).backward()
+    assert close64(dmin, m64.reshape(shp), H['pal_min'], what='PAL min distance')
+    assert close64(bev.grad, b64.grad.reshape(H['pal_grad_bev'].shape), H['pal_grad_bev'], what='PAL grad')
+
+
+def test_get_distance_bev_accepts_ragged_lists_like_the_reference(H):
+    """The real loss() call: a frame lists n_obj <= K clusters (centerpoint_head_gga.py:463-479,693);
+    the rows of the missing objects stay zero (:190-199) and receive no gradient."""
+    lists = _lists(H, 'cuda')
+    B, K = H['pal_bev'].shape[:2]
+    keep = [K - 5, K // 2]
+    ragged = [lists[b][:keep[b % 2]] for b in range(B)]
+    bev = torch.from_numpy(H['pal_bev']).cuda().requires_grad_(True)
+    dmin, dx, dy = G.get_distance_bev(ragged, bev)
+    assert dmin.shape == (B, K, 1)
+    for b in range(B):
+        n = keep[b % 2]
+        for got, key in ((dmin, 'pal_min'), (dx, 'pal_x'), (dy, 'pal_y')):
+            ref = H[key][b, :n]
+            assert np.allclose(got[b, :n].detach().cpu().numpy(), ref, rtol=1e-5, atol=1e-5 * max(1.0, np.abs(ref).max()))
+            assert (got[b, n:] == 0).all()
+    (dmin.sum() + dx.sum() + dy.sum()).backward()
+    for b in range(B):
+        assert (bev.grad[b, keep[b % 2]:] == 0).all() and bev.grad[b, :keep[b % 2]].abs().sum() > 0
+    with pytest.raises(AssertionError):
+        G.get_distance_bev([lists[0] + lists[0][:1]] + lists[1:], bev)      # more clusters than objects
 
 
 def test_point_box_alignment_vs_oracle_large_and_edge_cases():
@@ -80,9 +115,11 @@ def test_point_box_alignment_vs_oracle_large_and_edge_cases():
     (d * coef.cuda()).sum().backward()
     ref = torch.stack([rmin, rx, ry], 1).detach().numpy()
     got = d.detach().cpu().numpy()
-    assert np.allclose(got, ref, rtol=2e-5, atol=1e-4)
-    g, rg = gb.grad.cpu().numpy(), tb.grad.numpy()
-    assert np.allclose(g, rg, rtol=2e-4, atol=2e-5 * np.abs(rg).max())
+    b64 = d64(tb)
+    m64, x64, y64 = ol.point_box_distances(d64(xy), off, b64)
+    (torch.stack([m64, x64, y64], 1) * d64(coef)).sum().backward()
+    assert close64(got, torch.stack([m64, x64, y64], 1), ref, what='PAL distances (large)')
+    assert close64(gb.grad, b64.grad, tb.grad, what='PAL grad (large)')
     assert (got[counts == 0] == 0).all()
     # losses (weighted L1 against zero) agree with the oracle's mmdet restatement
     mask = torch.from_numpy((rng.uniform(size=(1, n_obj)) < 0.7).astype(np.float32))

@@ -11,6 +11,7 @@ from gga_b200.step import GeometryStep
 from oracle import geometry as og
 from oracle import losses as ol
 from oracle import membership as om
+from parity import close64
 
 pytestmark = pytest.mark.gpu
 F, N, M = 3, 6000, 200
@@ -28,17 +29,21 @@ def _oracle(bt):
     loss = ol.giou_loss_module(box2d, torch.from_numpy(bt['target']).reshape(-1, 4),
                                torch.from_numpy(bt['weight']).reshape(-1), avg_factor=float(F * M))
     loss.backward()
-    return masks, float(loss), b.grad.numpy()
+    b64 = torch.from_numpy(bt['boxes']).reshape(-1, 7).double().requires_grad_(True)
+    loss64 = ol.giou_loss_module(og.project_lidar_direct(b64, torch.from_numpy(bt['lidar2img']).reshape(-1, 4, 4).double()),
+                                 torch.from_numpy(bt['target']).reshape(-1, 4).double(),
+                                 torch.from_numpy(bt['weight']).reshape(-1).double(), avg_factor=float(F * M))
+    loss64.backward()
+    return masks, float(loss), b.grad.numpy(), float(loss64), b64.grad.numpy()
 
 
 def _check(step, bits, loss_sum, grad, ref):
-    masks, rloss, rgrad = ref
+    masks, rloss, rgrad, loss64, grad64 = ref
     got = G.unpack_bits(torch.as_tensor(bits).cuda(), M).cpu().numpy()
     assert np.array_equal(got, masks)                                  # bit-exact
     loss = float(loss_sum) / (F * M)
-    assert abs(loss - rloss) <= 1e-5 * abs(rloss) + 1e-7                # 1e-5 relative (north_star)
-    g = np.asarray(grad)
-    assert np.allclose(g, rgrad, rtol=1e-4, atol=1e-5 * np.abs(rgrad).max())
+    assert abs(loss - loss64) <= 1e-5 * abs(loss64) + 1e-7              # 1e-5 relative (north_star), float64 yardstick
+    assert close64(np.asarray(grad), grad64, rgrad, what='step grad')
 
 
 def test_step_matches_oracle_eager_graph_and_host():
@@ -75,6 +80,33 @@ def test_step_matches_oracle_eager_graph_and_host():
     _check(hs, dbits.cpu(), loss_sum, grad, ref)
     assert hs.host_bytes(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'],
                          masks_to_host=False)[1] == F * M * 7 * 4 + 4
+
+
+def test_hit_list_equals_dense_masks():
+    """The compact (row, box) pair list — from device rows and through the host-buffer step — names
+    exactly the set bits of the dense rows (order unspecified)."""
+    bt = _batch()
+    dev = torch.device('cuda:0')
+    t = {k: torch.from_numpy(v).to(dev) for k, v in bt.items()}
+    bits = G.points_in_boxes_bits(t['points'], t['boxes'])
+    dense = G.unpack_bits(bits, M).cpu().numpy().reshape(F * N, M)
+    want = np.stack(np.nonzero(dense), 1)
+    got = G.hit_list(bits, M).cpu().numpy()
+    assert got.shape == want.shape and got.dtype == np.int32
+    assert np.array_equal(got[np.lexsort((got[:, 1], got[:, 0]))], want)
+    with pytest.raises(RuntimeError):
+        G.hit_list(bits, M, capacity=max(1, len(want) // 2))      # overflow is reported, not silent
+    hin = {k: torch.from_numpy(v).pin_memory() for k, v in bt.items()}
+    hs = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
+    ref = _oracle(bt)
+    for _ in range(2):
+        hits, loss_sum, grad = hs.run_host(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'],
+                                           float(F * M), masks_to_host='hits')
+        h = hits.numpy()
+        assert np.array_equal(h[np.lexsort((h[:, 1], h[:, 0]))], want)
+        assert abs(loss_sum - ref[1] * F * M) <= 1e-5 * abs(ref[1] * F * M) + 1e-6
+    assert hs.host_bytes(hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'],
+                         masks_to_host='hits')[1] == 8 * len(want) + 4 + F * M * 7 * 4 + 4
 
 
 def test_membership_needs_no_scratch_and_is_repeatable():
