@@ -370,7 +370,8 @@ def run_steps_workload(args, x, cfg):
     split = cfg == 5 and args.partition == 'split' and world > 1
     N_full = N
     if split:   # the single frame's points are split across the ranks (boxes replicated)
-        lo, hi = G.dist.shard_range(N, rank, world)
+        from gga_b200 import dist as gdist
+        lo, hi = gdist.shard_range(N, rank, world)
         N = hi - lo
     W = G.row_words(M)
     member_bytes, all_bytes = step_bytes(F, N, M, W)
@@ -572,8 +573,8 @@ def run_steps_workload(args, x, cfg):
         e2e['masks_as_hit_list'] = {'value': ev3, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                                     'd2h_bytes_per_step': int(es.host_bytes(*eargs[:5], masks_to_host='hits')[1]),
                                     'ms_per_step': ems3}
-    except (TypeError, NotImplementedError):
-        pass
+    except (TypeError, NotImplementedError, RuntimeError) as e:   # e.g. the list did not fit its capacity
+        e2e['masks_as_hit_list'] = {'unavailable': str(e)[:160]}
 
     # the same membership through the mmcv-layout entry point (int32 [F, N, M], what a drop-in
     # `points_in_boxes_all` caller gets), reported beside the step's own kernel (never part of `value`)
@@ -693,15 +694,32 @@ def run_match_workload(args, x):
         graphs.append(g)
     torch.cuda.synchronize()
     packed = [torch.empty((F * M, 2), dtype=torch.float32, device=dev) for _ in range(n_sets)]
+    comm = torch.cuda.Stream() if world > 1 else None
+    comm_done = [None] * n_sets
+    if world > 1:
+        dist.all_gather_into_tensor(gathered.view(-1), packed[0].view(-1))   # communicator set-up
+        torch.cuda.synchronize()
 
     def run(K):
+        cur = torch.cuda.current_stream()
         for i in range(K):
             k = i % n_sets
+            if comm_done[k] is not None:
+                cur.wait_event(comm_done[k])      # the gather that read this set's results is done
             graphs[k].replay()
-            if world > 1:   # the pass's real exchange step: every rank ends up with all matches
-                packed[k][:, 0] = outs[k][0].float()
-                packed[k][:, 1] = outs[k][1]
-                dist.all_gather_into_tensor(gathered.view(-1), packed[k].view(-1))
+            if world > 1:   # the pass's real exchange step: every rank ends up with all matches;
+                # issued on a side stream so that it overlaps the next pass's kernels
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    packed[k][:, 0] = outs[k][0].float()
+                    packed[k][:, 1] = outs[k][1]
+                    dist.all_gather_into_tensor(gathered.view(-1), packed[k].view(-1))
+                    comm_done[k] = torch.cuda.Event()
+                    comm_done[k].record(comm)
+        if comm is not None:
+            cur.wait_stream(comm)
     run(max(args.warmup, 3))
     t0 = time.perf_counter()
     while time.perf_counter() - t0 < 0.25:

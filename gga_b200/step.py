@@ -166,7 +166,7 @@ class GeometryStep:
     def _run_host_hits(self, h, points, boxes, lidar2img, target, weight, avg_factor):
         L = self.L
         if 'h_hits' not in h:
-            cap = max(4096, 2 * self.F * self.N)
+            cap = min(max(4096, 8 * self.F * self.N), 1 << 26)   # 8 hits per point on average (dense indoor scenes ~5.5)
             h['h_hits'] = torch.empty((cap, 2), dtype=torch.int32).pin_memory()
             h['h_nhits'] = torch.zeros((1,), dtype=torch.int32).pin_memory()
         n = self.F * self.M

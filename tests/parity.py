@@ -9,7 +9,9 @@ at fp32 by tests/test_oracle_*.py, or the reference's own source text where it r
     max |got - f64|  <=  1e-5 * max |f64|
 
 If the reference's own fp32 evaluation is farther than that from the float64 value (an
-ill-conditioned case), its distance is the bound instead, and the case is printed.
+ill-conditioned case: e.g. a rotation gradient summed over thousands of signed per-point terms, where
+the fp32 per-term arithmetic the contract prescribes is the error), the case is printed and the bound
+becomes that distance plus the 1e-5 allowance (i.e. what "within 1e-5 of the fp32 reference" implies).
 """
 import numpy as np
 import torch
@@ -48,8 +50,8 @@ def close64(got, ref64, ref32=None, tol=TOL, what=''):
         e32 = float(np.abs(np64(ref32) - r).max())
         if e32 > bound:
             print(f'[parity] {what}: the fp32 reference is {e32 / scale:.2e} (relative) from its float64 value; '
-                  f'bound raised from {tol:.0e} to that')
-            bound = e32
+                  f'bound raised from {tol:.0e} to that + {tol:.0e}')
+            bound = e32 + tol * scale
     ok = err <= bound
     if not ok:
         i = np.unravel_index(np.abs(g - r).argmax(), r.shape)
