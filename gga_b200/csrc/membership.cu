@@ -158,18 +158,18 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {  // bar_addr: shared-space address
   uint32_t done = 0;
-  while (!done) {
+  do {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar_addr), "r"(parity)
         : "memory");
-  }
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
             if (outside_z(pt.z, a)) return;
             if (!inside_xy(pt.x, pt.y, a, terms[2 * t + 1])) return;
             if constexpr (MODE == kModePart) best = best < 0 ? (int)t : min(best, (int)t);
-            else row[t >> 5] |= 1u << (t & 31u);
+            else atomicOr(row + (t >> 5), 1u << (t & 31u));  // lane-private row: the atomic is just the shortest RMW
           };
           uint32_t cnt = e.y >> 24;
 #ifdef GGA_PROFILING
@@ -671,33 +671,37 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
         }
       };
 
+      // this warp's tiles: frame tile ft0 + k * dft, ring slot tr + R * (k mod S); everything advanced incrementally
+      const int dft = rf * R;
+      int ft = rr + rf * tr;
       int ks = 0;        // ring slot of this warp group's current tile: tr + R * ks
       uint32_t ph = 0u;  // mbarrier phase of the current pass over the ring
+      const uint32_t full0 = smem_u32(&s_full[tr]), empty0 = smem_u32(&s_empty[tr]);
+      const unsigned char* tile0 = ring + (size_t)tr * tile_bytes;
+      const int pin = tj * 32 + lane;  // this lane's point inside a tile
 #pragma unroll 1
-      for (int k = 0;; ++k) {
-        const int ft = rr + rf * (tr + R * k);  // tile of the frame
-        if (ft >= ntiles) break;
+      for (int k = 0; ft < ntiles; ++k, ft += dft) {
         const int gb = ft * kTileBatches + tj;
-        const int slot = tr + R * ks;
-        if (ft < n_full) {
-          mbar_wait(&s_full[slot], ph);
-          float4 pt;
-          const unsigned char* tile = ring + (size_t)slot * tile_bytes;
+        const bool ringed = ft < n_full;
+        float4 pt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ringed) {
+          mbar_wait_a(full0 + (uint32_t)(ks * R) * 8u, ph);
+          const unsigned char* tile = tile0 + (size_t)(ks * R) * tile_bytes;
           if constexpr (VEC4) {
-            pt = reinterpret_cast<const float4*>(tile)[tj * 32 + lane];
+            pt = reinterpret_cast<const float4*>(tile)[pin];
           } else {
-            const float* q = reinterpret_cast<const float*>(tile) + (size_t)(tj * 32 + lane) * p.pts_stride;
+            const float* q = reinterpret_cast<const float*>(tile) + (size_t)pin * p.pts_stride;
             pt = make_float4(q[0], q[1], q[2], 0.f);
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[slot]);
-          batch(pt, gb);
-          if (tj == 0 && lane == 0 && rr + rf * (tr + R * (k + S)) < n_full) {
-            mbar_wait(&s_empty[slot], ph);  // the 8 warps of this tile have read their points
-            request_tile(k + S, slot);
-          }
+          if (lane == 0) mbar_arrive_a(empty0 + (uint32_t)(ks * R) * 8u);
         } else if (gb < bpf) {
-          batch(load_pt(gb), gb);
+          pt = load_pt(gb);
+        }
+        if (gb < bpf) batch(pt, gb);
+        if (ringed && tj == 0 && lane == 0 && ft + dft * S < n_full) {
+          mbar_wait_a(empty0 + (uint32_t)(ks * R) * 8u, ph);  // the 8 warps of this tile have read their points
+          request_tile(k + S, tr + R * ks);
         }
         if (++ks == S) { ks = 0; ph ^= 1u; }
       }

@@ -12,14 +12,10 @@ fi
 Q="timeout 300 python tools/quick_bench.py"
 {
 $Q --cfg 2
-$Q --cfg 2 --unsorted
+$Q --cfg 2
 $Q --cfg 1 --frames 8
 $Q --cfg 3
 $Q --cfg 5
-$Q --cfg 2 --mode part
-$Q --cfg 2 --mode all
-export GGA_B200_LIB=$PWD/gga_b200/_C/libgga_b200_prof.so
-$Q --cfg 2 --nt 1024 --variant 0 --trace
-$Q --cfg 2 --nt 1024 --variant 1,8,9
+timeout 300 ncu --metrics smsp__inst_executed.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:pib_sweep -s 20 -c 2 python tools/quick_bench.py --cfg 2 2>&1 | grep -E "inst_executed|time_duration|issue_active"
 } > gpurun_out/${TAG}_qb.log 2>&1
 cat gpurun_out/${TAG}_qb.log
