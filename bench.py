@@ -345,6 +345,20 @@ def setup_dist():
     return x
 
 
+def ramp_reps(x, fn, seconds=0.25):
+    """How often to repeat fn() so that ~`seconds` of this work run before the timed region (SM clock
+    ramp).  fn may hold collectives, so every rank must repeat it the SAME number of times: the count
+    is derived from one probe run and agreed on through a max over ranks."""
+    import math
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fn()
+    torch.cuda.synchronize()
+    t1 = x.max_over_ranks(time.perf_counter() - t0)
+    return int(min(5000, max(1, math.ceil(seconds / max(t1, 1e-6)))))
+
+
 def timed(x, fn, sampler=None):
     """barrier + sync, CUDA events around fn() on the current stream, barrier + sync; max over ranks (ms)."""
     import torch
@@ -473,8 +487,7 @@ def run_steps_workload(args, x, cfg):
     # warm-up: at least W steps, and at least ~0.25 s of this same work so that the clocks have ramped
     # (the driver's default run times only 20 steps = 0.3 ms of GPU work after a long host set-up)
     warm()
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.25:
+    for _ in range(ramp_reps(x, main_run)):
         main_run()
         torch.cuda.synchronize()
     for wk in works:
@@ -542,39 +555,62 @@ def run_steps_workload(args, x, cfg):
         pass
 
     # end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    hb = host[0]
-    hin = {name: torch.from_numpy(np.ascontiguousarray(hb[name])).pin_memory() for name in names}
-    es = GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct')
-    eargs = (hin['points'], hin['boxes'], hin['lidar2img'], hin['target'], hin['weight'], float(F * M))
-    ereps = max(5, min(args.steps, 40))
+    # Two batches alternate (own pinned inputs, own GeometryStep = own device context and pinned
+    # result buffers): `pipelined` submits batch k+1 before it waits for batch k, so the H2D copies of
+    # one batch overlap the D2H copies of the previous one (what a prefetching data loader does);
+    # `synchronous` is one blocking run_host call per step.
+    depth = max(2, args.e2e_depth)
+    hins = [{name: torch.from_numpy(np.ascontiguousarray(host[k % len(host)][name])).pin_memory() for name in names}
+            for k in range(2)]
+    ess = [GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct') for _ in range(depth)]
+    eargs = [(h['points'], h['boxes'], h['lidar2img'], h['target'], h['weight'], float(F * M)) for h in hins]
+    ereps = max(3 * depth, min(args.steps, 40))
+    es = ess[0]
 
-    def e2e_leg(**kw):
-        for _ in range(3):
-            es.run_host(*eargs, n_streams=args.e2e_streams, **kw)
+    def e2e_leg(pipelined=True, **kw):
+        # pipelined steps overlap each other, so each is ONE copy each way + one launch (n_streams = 1);
+        # a blocking step overlaps its own frames over a few streams instead
+        kw = dict(kw, n_streams=args.e2e_pipe_streams if pipelined else args.e2e_streams)
+        for k in range(2 * depth):
+            ess[k % depth].run_host(*eargs[k % 2], **kw)
 
-        def loop():
-            for _ in range(ereps):
-                es.run_host(*eargs, n_streams=args.e2e_streams, **kw)
-        ems = timed(x, loop)
+        def loop_sync():
+            for k in range(ereps):
+                ess[k % depth].run_host(*eargs[k % 2], **kw)
+
+        def loop_pipe():
+            for k in range(ereps):
+                if k >= depth:
+                    ess[k % depth].wait_host()          # batch k - depth
+                ess[k % depth].submit_host(*eargs[k % 2], **kw)
+            for k in range(ereps, ereps + depth):
+                ess[k % depth].wait_host()
+        ems = timed(x, loop_pipe if pipelined else loop_sync)
         return round(frames_step_global * ereps / (ems * 1e-3), 1), round(ems / ereps, 4)
     ev, ems_step = e2e_leg()
-    h2d, d2h = es.host_bytes(*eargs[:5])
+    evs, ems_sync = e2e_leg(pipelined=False)
+    h2d, d2h = es.host_bytes(*eargs[0][:5])
     e2e = {'value': ev, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h), 'steps': ereps,
-           'ms_per_step': ems_step,
-           'returns': 'masks + loss + box gradients to host memory (the points_in_boxes_cpu-style contract)'}
+           'ms_per_step': ems_step, 'pipeline_depth': depth,
+           'returns': 'masks + loss + box gradients to host memory (the points_in_boxes_cpu-style contract)',
+           'synchronous': {'value': evs, 'unit': UNIT, 'ms_per_step': ems_sync}}
     # same call with the masks left on the device (the training use: only loss and gradients go back)
     ev2, ems2 = e2e_leg(masks_to_host=False)
+    ev2s, ems2s = e2e_leg(pipelined=False, masks_to_host=False)
     e2e['masks_on_device'] = {'value': ev2, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                              'd2h_bytes_per_step': int(es.host_bytes(*eargs[:5], masks_to_host=False)[1]),
-                              'ms_per_step': ems2}
+                              'd2h_bytes_per_step': int(es.host_bytes(*eargs[0][:5], masks_to_host=False)[1]),
+                              'ms_per_step': ems2, 'synchronous': {'value': ev2s, 'ms_per_step': ems2s}}
     # ... and with the masks returned as a compact hit list (point, box) instead of dense bit rows
     try:
         ev3, ems3 = e2e_leg(masks_to_host='hits')
+        ev3s, ems3s = e2e_leg(pipelined=False, masks_to_host='hits')
         e2e['masks_as_hit_list'] = {'value': ev3, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-                                    'd2h_bytes_per_step': int(es.host_bytes(*eargs[:5], masks_to_host='hits')[1]),
-                                    'ms_per_step': ems3}
+                                    'd2h_bytes_per_step': int(es.host_bytes(*eargs[0][:5], masks_to_host='hits')[1]),
+                                    'ms_per_step': ems3, 'synchronous': {'value': ev3s, 'ms_per_step': ems3s}}
     except (TypeError, NotImplementedError, RuntimeError) as e:   # e.g. the list did not fit its capacity
         e2e['masks_as_hit_list'] = {'unavailable': str(e)[:160]}
+    for s_ in ess:
+        s_.close()
 
     # the same membership through the mmcv-layout entry point (int32 [F, N, M], what a drop-in
     # `points_in_boxes_all` caller gets), reported beside the step's own kernel (never part of `value`)
@@ -721,8 +757,7 @@ def run_match_workload(args, x):
         if comm is not None:
             cur.wait_stream(comm)
     run(max(args.warmup, 3))
-    t0 = time.perf_counter()
-    while time.perf_counter() - t0 < 0.25:
+    for _ in range(ramp_reps(x, lambda: run(args.steps))):
         run(args.steps)
         torch.cuda.synchronize()
     sampler = ClockSampler(physical_gpu_index(x.local))
@@ -799,7 +834,9 @@ def main():
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
     ap.add_argument('--partition', default='replicate', choices=['replicate', 'split'], help='c5 across ranks')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-streams', type=int, default=3)
+    ap.add_argument('--e2e-streams', type=int, default=3, help='streams of the frame pipeline inside a blocking host step')
+    ap.add_argument('--e2e-depth', type=int, default=3, help='host-buffer steps kept in flight (alternating contexts)')
+    ap.add_argument('--e2e-pipe-streams', type=int, default=1, help='streams inside a pipelined host step (1 = one copy each way)')
     ap.add_argument('--lanes', type=int, default=2, help='independent steps in flight on one GPU (parallel graph branches)')
     args = ap.parse_args()
     if args.impl == 'reference':

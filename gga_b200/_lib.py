@@ -86,6 +86,10 @@ SIGNATURES = {
     'gga_step_create': ([c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)], c_int),
     'gga_step_destroy': ([c_void_p], c_int),
     'gga_step_device_bits': ([c_void_p, ctypes.POINTER(c_void_p)], c_int),
+    'gga_step_submit_host': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                              ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                              c_void_p, c_int, c_void_p, c_void_p], c_int),
+    'gga_step_wait_host': ([c_void_p, c_void_p, c_void_p], c_int),
     'gga_step_run_host_hits': ([c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                 ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p], c_int),

@@ -34,7 +34,10 @@ struct StepCtx {
   size_t scratch_bytes;
   int32_t* d_pairs;   // [pair_capacity, 2] hit list of the masks (allocated on first use)
   int32_t* d_count;   // [1]
+  int32_t* h_count;   // [1] page-locked: the number of pairs of the step in flight
   int pair_capacity;
+  bool pending;       // a submitted step has not been waited for
+  int pending_hits;   // its hit capacity (0: dense rows or masks left on the device)
   cudaStream_t streams[kMaxStreams];
   cudaStream_t box_stream;
   cudaEvent_t boxes_ready, done[kMaxStreams], box_done;
@@ -42,11 +45,16 @@ struct StepCtx {
 
 void destroy(StepCtx* c) {
   if (!c) return;
+  if (c->pending) {  // host buffers of a step in flight must not be referenced after destroy
+    cudaStreamSynchronize(c->box_stream);
+    for (int i = 0; i < c->n_streams; ++i) cudaStreamSynchronize(c->streams[i]);
+  }
   cudaFree(c->d_points); cudaFree(c->d_boxes); cudaFree(c->d_proj); cudaFree(c->d_target); cudaFree(c->d_weight);
   cudaFree(c->d_bits); cudaFree(c->d_box2d); cudaFree(c->d_loss); cudaFree(c->d_loss_sum); cudaFree(c->d_grad);
   cudaFree(c->d_scratch);
   if (c->d_pairs) cudaFree(c->d_pairs);
   if (c->d_count) cudaFree(c->d_count);
+  if (c->h_count) cudaFreeHost(c->h_count);
   for (int i = 0; i < kMaxStreams; ++i) {
     if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
     if (c->done[i]) cudaEventDestroy(c->done[i]);
@@ -118,8 +126,25 @@ static int enqueue_step(StepCtx* c, const float* points, const float* boxes, con
   // boxes first: every frame's membership needs them
   GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_boxes, boxes, F * M * 7 * sizeof(float), cudaMemcpyHostToDevice, c->box_stream));
   GGA_CHECK_CUDA(cudaEventRecord(c->boxes_ready, c->box_stream));
+  if (c->n_streams == 1) {
+    // One piece: a single copy each way and ONE membership launch over all frames.  Nothing overlaps
+    // inside the step — meant for callers that keep several steps in flight (gga_step_submit_host on
+    // alternating contexts), where the copies of different steps overlap and fewer, larger copies win.
+    cudaStream_t q = c->streams[0];
+    GGA_CHECK_CUDA(cudaStreamWaitEvent(q, c->boxes_ready, 0));
+    GGA_CHECK_CUDA(cudaMemcpyAsync(c->d_points, points, F * N * st * sizeof(float), cudaMemcpyHostToDevice, q));
+    const int rc = gga_points_in_boxes_bits(c->d_points, (int)st, c->d_boxes, c->d_bits, (int)F, (int)N, (int)M, q);
+    if (rc != GGA_OK) return rc;
+    if (bits)
+      GGA_CHECK_CUDA(cudaMemcpyAsync(bits, c->d_bits, F * N * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, q));
+    if (hits) {
+      const int rc2 = gga_pib_hit_list(c->d_bits, (int64_t)(F * N), (int)M, 0, c->d_pairs, c->pair_capacity, c->d_count, 0, q);
+      if (rc2 != GGA_OK) return rc2;
+    }
+    GGA_CHECK_CUDA(cudaEventRecord(c->done[0], q));
+  }
   // membership, one frame per pipeline slot
-  for (size_t f = 0; f < F; ++f) {
+  for (size_t f = 0; f < F && c->n_streams > 1; ++f) {
     const int s = (int)(f % c->n_streams);
     cudaStream_t q = c->streams[s];
     GGA_CHECK_CUDA(cudaStreamWaitEvent(q, c->boxes_ready, 0));
@@ -158,32 +183,100 @@ static int enqueue_step(StepCtx* c, const float* points, const float* boxes, con
   return GGA_OK;
 }
 
-extern "C" int gga_step_run_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
-                                 const float* target, const float* weight, int proj_mode, int loss_kind,
-                                 float loss_weight, float avg_factor, float eps, float depth_clamp,
-                                 uint32_t* bits, float* loss_sum, float* grad_boxes) {
-  StepCtx* c = static_cast<StepCtx*>(ctx);
-  GGA_REQUIRE(c != nullptr, "null context");
-  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes, "null host pointer");
-  GGA_REQUIRE(avg_factor > 0.f, "avg_factor must be positive");
-  int dev = 0;
-  GGA_CHECK_CUDA(cudaGetDevice(&dev));
-  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
-  const int rc = enqueue_step(c, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight,
-                              avg_factor, eps, depth_clamp, bits, false, loss_sum, grad_boxes);
-  // The call is synchronous, like the CPU op it stands in for — and on a failure half-way the
-  // copies already enqueued still reference the caller's host buffers: drain every stream first.
+// Drains every stream of the context; returns the first CUDA error seen.
+static cudaError_t drain(StepCtx* c) {
   cudaError_t e = cudaStreamSynchronize(c->box_stream);
   for (int s = 0; s < c->n_streams; ++s) {
     const cudaError_t es = cudaStreamSynchronize(c->streams[s]);
     if (e == cudaSuccess) e = es;
   }
-  if (rc != GGA_OK) return rc;
+  return e;
+}
+
+extern "C" int gga_step_submit_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                                    const float* target, const float* weight, int proj_mode, int loss_kind,
+                                    float loss_weight, float avg_factor, float eps, float depth_clamp,
+                                    uint32_t* bits, int hit_capacity, float* loss_sum, float* grad_boxes) {
+  StepCtx* c = static_cast<StepCtx*>(ctx);
+  GGA_REQUIRE(c != nullptr, "null context");
+  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes, "null host pointer");
+  GGA_REQUIRE(avg_factor > 0.f && hit_capacity >= 0, "avg_factor must be positive, hit_capacity non-negative");
+  GGA_REQUIRE(!c->pending, "the context already has a step in flight: call gga_step_wait_host first");
+  int dev = 0;
+  GGA_CHECK_CUDA(cudaGetDevice(&dev));
+  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
+  const bool hits = hit_capacity > 0;
+  if (hits && c->pair_capacity < hit_capacity) {  // (re)allocated outside the pipeline, first use only
+    GGA_CHECK_CUDA(cudaDeviceSynchronize());
+    if (c->d_pairs) cudaFree(c->d_pairs);
+    c->d_pairs = nullptr;
+    c->pair_capacity = 0;
+    GGA_CHECK_CUDA(cudaMalloc(&c->d_pairs, (size_t)hit_capacity * 2 * sizeof(int32_t)));
+    if (!c->d_count) GGA_CHECK_CUDA(cudaMalloc(&c->d_count, sizeof(int32_t)));
+    if (!c->h_count) GGA_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&c->h_count), sizeof(int32_t), cudaHostAllocDefault));
+    c->pair_capacity = hit_capacity;
+  }
+  int rc = enqueue_step(c, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight, avg_factor,
+                        eps, depth_clamp, bits, hits, loss_sum, grad_boxes);
+  if (rc == GGA_OK && hits) {  // the number of pairs, once every frame's list kernel is done
+    cudaStream_t b = c->box_stream;
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < c->n_streams && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(b, c->done[s], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_count, c->d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, b);
+    if (e != cudaSuccess) {
+      gga_set_error("gga_step_submit_host: %s", cudaGetErrorString(e));
+      rc = GGA_ERR_CUDA;
+    }
+  }
+  if (rc != GGA_OK) {
+    // on a failure half-way the copies already enqueued still reference the caller's host buffers
+    drain(c);
+    return rc;
+  }
+  c->pending = true;
+  c->pending_hits = hits ? hit_capacity : 0;
+  return GGA_OK;
+}
+
+extern "C" int gga_step_wait_host(void* ctx, int32_t* hits, int32_t* n_hits) {
+  StepCtx* c = static_cast<StepCtx*>(ctx);
+  GGA_REQUIRE(c != nullptr, "null context");
+  GGA_REQUIRE(c->pending, "no step in flight");
+  c->pending = false;
+  cudaError_t e = drain(c);
   if (e != cudaSuccess) {
-    gga_set_error("gga_step_run_host: %s", cudaGetErrorString(e));
+    gga_set_error("gga_step_wait_host: %s", cudaGetErrorString(e));
     return GGA_ERR_CUDA;
   }
+  if (c->pending_hits > 0) {
+    GGA_REQUIRE(hits != nullptr && n_hits != nullptr, "the step was submitted with a hit list: hits and n_hits are required");
+    const int cap = c->pending_hits;
+    *n_hits = *c->h_count;
+    const int n = *n_hits < cap ? *n_hits : cap;
+    if (n > 0) {  // exactly that many pairs
+      e = cudaMemcpyAsync(hits, c->d_pairs, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->box_stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(c->box_stream);
+      if (e != cudaSuccess) {
+        gga_set_error("gga_step_wait_host: %s", cudaGetErrorString(e));
+        return GGA_ERR_CUDA;
+      }
+    }
+    if (*n_hits > cap) {
+      gga_set_error("hit list overflow: %d pairs, capacity %d", *n_hits, cap);
+      return GGA_ERR_UNSUPPORTED;
+    }
+  }
   return GGA_OK;
+}
+
+// The synchronous forms, like the CPU op they stand in for: submit + wait.
+extern "C" int gga_step_run_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                                 const float* target, const float* weight, int proj_mode, int loss_kind,
+                                 float loss_weight, float avg_factor, float eps, float depth_clamp,
+                                 uint32_t* bits, float* loss_sum, float* grad_boxes) {
+  const int rc = gga_step_submit_host(ctx, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight,
+                                      avg_factor, eps, depth_clamp, bits, 0, loss_sum, grad_boxes);
+  return rc != GGA_OK ? rc : gga_step_wait_host(ctx, nullptr, nullptr);
 }
 
 extern "C" int gga_step_run_host_hits(void* ctx, const float* points, const float* boxes, const float* lidar2img,
@@ -191,50 +284,11 @@ extern "C" int gga_step_run_host_hits(void* ctx, const float* points, const floa
                                       float loss_weight, float avg_factor, float eps, float depth_clamp,
                                       int32_t* hits, int hit_capacity, int32_t* n_hits, float* loss_sum,
                                       float* grad_boxes) {
-  StepCtx* c = static_cast<StepCtx*>(ctx);
-  GGA_REQUIRE(c != nullptr, "null context");
-  GGA_REQUIRE(points && boxes && lidar2img && target && loss_sum && grad_boxes && hits && n_hits, "null host pointer");
-  GGA_REQUIRE(avg_factor > 0.f && hit_capacity > 0, "avg_factor and hit_capacity must be positive");
-  int dev = 0;
-  GGA_CHECK_CUDA(cudaGetDevice(&dev));
-  GGA_REQUIRE(dev == c->device, "context belongs to device %d, current device is %d", c->device, dev);
-  if (c->pair_capacity < hit_capacity) {  // (re)allocated outside the pipeline, first use only
-    GGA_CHECK_CUDA(cudaDeviceSynchronize());
-    if (c->d_pairs) cudaFree(c->d_pairs);
-    c->d_pairs = nullptr;
-    c->pair_capacity = 0;
-    GGA_CHECK_CUDA(cudaMalloc(&c->d_pairs, (size_t)hit_capacity * 2 * sizeof(int32_t)));
-    if (!c->d_count) GGA_CHECK_CUDA(cudaMalloc(&c->d_count, sizeof(int32_t)));
-    c->pair_capacity = hit_capacity;
-  }
-  int rc = enqueue_step(c, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight, avg_factor,
-                        eps, depth_clamp, nullptr, true, loss_sum, grad_boxes);
-  cudaError_t e = cudaSuccess;
-  if (rc == GGA_OK) {  // the count first (all frame streams joined), then exactly that many pairs
-    cudaStream_t b = c->box_stream;
-    for (int s = 0; s < c->n_streams && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(b, c->done[s], 0);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(n_hits, c->d_count, sizeof(int32_t), cudaMemcpyDeviceToHost, b);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(b);
-    if (e == cudaSuccess) {
-      const int n = *n_hits < hit_capacity ? *n_hits : hit_capacity;
-      if (n > 0) e = cudaMemcpyAsync(hits, c->d_pairs, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, b);
-    }
-  }
-  cudaError_t e1 = cudaStreamSynchronize(c->box_stream);
-  for (int s = 0; s < c->n_streams; ++s) {
-    const cudaError_t es = cudaStreamSynchronize(c->streams[s]);
-    if (e1 == cudaSuccess) e1 = es;
-  }
-  if (rc != GGA_OK) return rc;
-  if (e != cudaSuccess || e1 != cudaSuccess) {
-    gga_set_error("gga_step_run_host_hits: %s", cudaGetErrorString(e != cudaSuccess ? e : e1));
-    return GGA_ERR_CUDA;
-  }
-  if (*n_hits > hit_capacity) {
-    gga_set_error("hit list overflow: %d pairs, capacity %d", *n_hits, hit_capacity);
-    return GGA_ERR_UNSUPPORTED;
-  }
-  return GGA_OK;
+  GGA_REQUIRE(hits && n_hits, "null host pointer");
+  GGA_REQUIRE(hit_capacity > 0, "hit_capacity must be positive");
+  const int rc = gga_step_submit_host(ctx, points, boxes, lidar2img, target, weight, proj_mode, loss_kind, loss_weight,
+                                      avg_factor, eps, depth_clamp, nullptr, hit_capacity, loss_sum, grad_boxes);
+  return rc != GGA_OK ? rc : gga_step_wait_host(ctx, hits, n_hits);
 }
 
 extern "C" int gga_step_device_bits(void* ctx, uint32_t** bits_device) {

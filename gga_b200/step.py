@@ -120,6 +120,20 @@ class GeometryStep:
             a.loss_accum = self.loss_accum.data_ptr()
         return a
 
+    def _host_ctx(self, n_streams):
+        if self._host is None or self._host['n_streams'] != n_streams:
+            self.close()
+            ctx = _lib.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self.L.gga_step_create(self.F, self.N, self.M, self.pts_stride, int(n_streams),
+                                                  ctypes.byref(ctx)), 'step_create')
+            self._host = dict(
+                ctx=ctx, n_streams=n_streams, in_flight=None,
+                h_bits=torch.empty(self.bits.shape, dtype=torch.int32).pin_memory(),
+                h_grad=torch.empty(self.grad_boxes.shape, dtype=torch.float32).pin_memory(),
+                h_loss=torch.empty((1,), dtype=torch.float32).pin_memory())
+        return self._host
+
     def run_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3, masks_to_host=True):
         """Same step with HOST inputs (page-locked torch CPU tensors) and HOST results: returns
         (bits_host int32 [F,N,W], loss_sum float, grad_boxes_host [F*M,7]).  Synchronous.
@@ -133,52 +147,52 @@ class GeometryStep:
         training shape), so the library pipelines the step frame by frame over `n_streams`
         streams — the H2D copy of frame f+1, the membership kernels of frame f and the D2H copy
         of the masks of frame f-1 overlap (full-duplex link)."""
+        self.submit_host(points, boxes, lidar2img, target, weight, avg_factor, n_streams, masks_to_host)
+        return self.wait_host()
+
+    def submit_host(self, points, boxes, lidar2img, target, weight, avg_factor=None, n_streams=3, masks_to_host=True):
+        """Asynchronous half of ``run_host``: enqueues the step (copies included) and returns.  The
+        input tensors must stay alive and unmodified until ``wait_host()``, which returns what
+        ``run_host`` returns.  One step in flight per ``GeometryStep``; two of them used alternately
+        (``a.submit_host(batch k+1)`` before ``b.wait_host()`` of batch k) overlap the H2D copies
+        of one batch with the D2H copies of the previous one — the PCIe link is full duplex."""
         L = self.L
-        if self._host is None or self._host['n_streams'] != n_streams:
-            self.close()
-            ctx = _lib.c_void_p()
-            with torch.cuda.device(self.device):
-                _lib.check(L.gga_step_create(self.F, self.N, self.M, self.pts_stride, int(n_streams),
-                                             ctypes.byref(ctx)), 'step_create')
-            self._host = dict(
-                ctx=ctx, n_streams=n_streams,
-                h_bits=torch.empty(self.bits.shape, dtype=torch.int32).pin_memory(),
-                h_grad=torch.empty(self.grad_boxes.shape, dtype=torch.float32).pin_memory(),
-                h_loss=torch.empty((1,), dtype=torch.float32).pin_memory())
-        h = self._host
+        h = self._host_ctx(n_streams)
         for t in (points, boxes, lidar2img, target, weight):
             assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()), \
                 'run_host takes contiguous fp32 CPU tensors'
+        cap = 0
         if masks_to_host == 'hits':
-            return self._run_host_hits(h, points, boxes, lidar2img, target, weight, avg_factor)
+            if 'h_hits' not in h:
+                n_cap = min(max(4096, 8 * self.F * self.N), 1 << 26)   # 8 hits per point on average (dense indoor scenes ~5.5)
+                h['h_hits'] = torch.empty((n_cap, 2), dtype=torch.int32).pin_memory()
+                h['h_nhits'] = torch.zeros((1,), dtype=torch.int32).pin_memory()
+            cap = h['h_hits'].shape[0]
         n = self.F * self.M
         with torch.cuda.device(self.device):
-            _lib.check(L.gga_step_run_host(
+            _lib.check(L.gga_step_submit_host(
                 h['ctx'], points.data_ptr(), boxes.data_ptr(), lidar2img.data_ptr(), target.data_ptr(),
                 None if weight is None else weight.data_ptr(), self.mode, self.kind, self.loss_weight,
                 float(avg_factor if avg_factor is not None else max(n, 1)), self.eps, self.depth_clamp,
-                h['h_bits'].data_ptr() if masks_to_host else None, h['h_loss'].data_ptr(), h['h_grad'].data_ptr()),
-                'step_run_host')
+                h['h_bits'].data_ptr() if masks_to_host is True else None, cap, h['h_loss'].data_ptr(),
+                h['h_grad'].data_ptr()), 'step_submit_host')
+        h['in_flight'] = (masks_to_host, (points, boxes, lidar2img, target, weight))   # keeps the inputs alive
+
+    def wait_host(self):
+        h = self._host
+        assert h is not None and h.get('in_flight') is not None, 'no step in flight'
+        masks_to_host, _ = h['in_flight']
+        h['in_flight'] = None
+        hits = masks_to_host == 'hits'
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.gga_step_wait_host(h['ctx'], h['h_hits'].data_ptr() if hits else None,
+                                                 h['h_nhits'].data_ptr() if hits else None), 'step_wait_host')
+        if hits:
+            self.last_hits = int(h['h_nhits'][0])
+            return h['h_hits'][:self.last_hits], float(h['h_loss'][0]), h['h_grad']
         if not masks_to_host:
             return self._device_bits(), float(h['h_loss'][0]), h['h_grad']
         return h['h_bits'], float(h['h_loss'][0]), h['h_grad']
-
-    def _run_host_hits(self, h, points, boxes, lidar2img, target, weight, avg_factor):
-        L = self.L
-        if 'h_hits' not in h:
-            cap = min(max(4096, 8 * self.F * self.N), 1 << 26)   # 8 hits per point on average (dense indoor scenes ~5.5)
-            h['h_hits'] = torch.empty((cap, 2), dtype=torch.int32).pin_memory()
-            h['h_nhits'] = torch.zeros((1,), dtype=torch.int32).pin_memory()
-        n = self.F * self.M
-        with torch.cuda.device(self.device):
-            _lib.check(L.gga_step_run_host_hits(
-                h['ctx'], points.data_ptr(), boxes.data_ptr(), lidar2img.data_ptr(), target.data_ptr(),
-                None if weight is None else weight.data_ptr(), self.mode, self.kind, self.loss_weight,
-                float(avg_factor if avg_factor is not None else max(n, 1)), self.eps, self.depth_clamp,
-                h['h_hits'].data_ptr(), h['h_hits'].shape[0], h['h_nhits'].data_ptr(), h['h_loss'].data_ptr(),
-                h['h_grad'].data_ptr()), 'step_run_host_hits')
-        self.last_hits = int(h['h_nhits'][0])
-        return h['h_hits'][:self.last_hits], float(h['h_loss'][0]), h['h_grad']
 
     def _device_bits(self):
         h = self._host

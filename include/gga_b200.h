@@ -322,7 +322,8 @@ int gga_pack_targets(const gga_target_args* args, void* stream);
  * /root/reference/mmdet3d/ops/__init__.py:12,38 extended to the whole loss step of
  * mmdet3d/models/dense_heads/centerpoint_head_gga.py:629-723): H2D copies, membership masks,
  * projection + loss forward/backward, D2H copies — pipelined frame by frame over `n_streams`
- * streams (the PCIe link is the bound).  A context owns every device buffer, stream and
+ * streams (the PCIe link is the bound); n_streams == 1 means ONE copy each way and one membership
+ * launch over all frames (for callers that overlap whole steps with gga_step_submit_host).  A context owns every device buffer, stream and
  * event of one (frames, points, boxes) shape on the current device; run calls allocate nothing
  * and are synchronous.  Host buffers should be page-locked for the copies to overlap.
  *   points [F, N, pts_stride], boxes [F, M, 7], lidar2img [F, M, 16] (one 4x4 per object),
@@ -344,6 +345,18 @@ int gga_step_run_host_hits(void* ctx, const float* points, const float* boxes, c
                            const float* target, const float* weight, int proj_mode, int loss_kind,
                            float loss_weight, float avg_factor, float eps, float depth_clamp,
                            int32_t* hits, int hit_capacity, int32_t* n_hits, float* loss_sum, float* grad_boxes);
+/* Asynchronous form.  submit enqueues the whole step and returns; EVERY host buffer passed to it
+ * (inputs and results) must stay valid and untouched until gga_step_wait_host(ctx, ...) has returned.
+ * A context holds one step in flight (GGA_ERR_INVALID otherwise); two contexts used alternately keep
+ * both directions of the PCIe link busy: the H2D copies of step k+1 overlap the D2H copies of step k.
+ * hit_capacity > 0 asks for the hit list (normally with `bits` NULL, i.e. instead of dense rows); its pairs
+ * are delivered by wait (hits [hit_capacity, 2], *n_hits), which may be NULL otherwise.
+ * gga_step_run_host / _run_host_hits are submit + wait. */
+int gga_step_submit_host(void* ctx, const float* points, const float* boxes, const float* lidar2img,
+                         const float* target, const float* weight, int proj_mode, int loss_kind,
+                         float loss_weight, float avg_factor, float eps, float depth_clamp,
+                         uint32_t* bits, int hit_capacity, float* loss_sum, float* grad_boxes);
+int gga_step_wait_host(void* ctx, int32_t* hits, int32_t* n_hits);
 /* `bits` may be NULL: the masks then stay on the device (the training use — the reference's GPU op
  * `points_in_boxes_all` leaves them there too, base_box3d.py:566) and only loss and gradients come
  * back.  gga_step_device_bits() gives the device buffer [F, N, W] they are in, valid until the

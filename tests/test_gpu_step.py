@@ -109,6 +109,46 @@ def test_hit_list_equals_dense_masks():
                          masks_to_host='hits')[1] == 8 * len(want) + 4 + F * M * 7 * 4 + 4
 
 
+@pytest.mark.parametrize('n_streams', [1, 3])
+def test_pipelined_host_steps_equal_synchronous_ones(n_streams):
+    """submit_host / wait_host: two contexts used alternately on two different batches (batch k+1 is
+    submitted before batch k is waited for) return what the blocking call returns, for dense rows,
+    masks left on the device and the hit list; a second submit on a busy context is refused."""
+    dev = torch.device('cuda:0')
+    bts = []
+    for seed in (40, 41):
+        bt = synth.make_batch(2, seed, F, N=N, M=M)
+        bts.append({k: np.ascontiguousarray(bt[k]) for k in ('points', 'boxes', 'lidar2img', 'target', 'weight')})
+    refs = [_oracle(bt) for bt in bts]
+    hins = [{k: torch.from_numpy(v).pin_memory() for k, v in bt.items()} for bt in bts]
+    args = [(h['points'], h['boxes'], h['lidar2img'], h['target'], h['weight'], float(F * M)) for h in hins]
+    ss = [GeometryStep(F, N, M, dev, kind='giou', mode='lidar_direct') for _ in range(2)]
+    for mode in (True, False, 'hits'):
+        ss[0].submit_host(*args[0], masks_to_host=mode, n_streams=n_streams)
+        for k in range(1, 6):
+            ss[k % 2].submit_host(*args[k % 2], masks_to_host=mode, n_streams=n_streams)
+            j = (k - 1) % 2
+            out, loss_sum, grad = ss[j].wait_host()
+            if mode == 'hits':
+                h = out.numpy()
+                dense = np.zeros((F * N, M), dtype=np.int32)
+                dense[h[:, 0], h[:, 1]] = 1
+                assert len(h) == refs[j][0].sum() and np.array_equal(dense.reshape(F, N, M), refs[j][0])
+                assert abs(loss_sum / (F * M) - refs[j][3]) <= 1e-5 * abs(refs[j][3]) + 1e-7
+            else:
+                _check(ss[j], out.cpu() if out.is_cuda else out, loss_sum, grad, refs[j])
+        ss[5 % 2].wait_host()
+    ss[0].submit_host(*args[0], n_streams=n_streams)
+    with pytest.raises(RuntimeError, match='in flight'):
+        ss[0].submit_host(*args[0], n_streams=n_streams)
+    ss[0].wait_host()
+    with pytest.raises(AssertionError):
+        ss[0].wait_host()
+    ss[1].submit_host(*args[1], n_streams=n_streams)
+    for s in ss:
+        s.close()          # a context destroyed with a step in flight drains it first
+
+
 def test_membership_needs_no_scratch_and_is_repeatable():
     """The membership call owns no global scratch: the same call twice into a poisoned output
     buffer gives the same exact rows (dense SUN-RGBD-like scene, 512 boxes = 16-word rows)."""

@@ -56,6 +56,31 @@ def main():
             print(json.dumps(dict(streams=ns, ms=round(ms, 4), frames_per_s=round(F / ms * 1e3, 1))), flush=True)
             s.close()
 
+    # pipelined: `depth` contexts used in turn, batch k+1 .. k+depth-1 submitted before batch k is waited for
+    for mode in (True, False, 'hits'):
+        for depth in (2, 3, 4):
+            for ns in (1, 2):
+                ss = [GeometryStep(F, N, M, 'cuda', kind='giou', mode='lidar_direct') for _ in range(depth)]
+                for s in ss:
+                    s.run_host(*args, n_streams=ns, masks_to_host=mode)
+
+                def loop(reps=30):
+                    for k in range(reps):
+                        if k >= depth:
+                            ss[k % depth].wait_host()
+                        ss[k % depth].submit_host(*args, n_streams=ns, masks_to_host=mode)
+                    for k in range(reps, reps + depth):
+                        ss[k % depth].wait_host()
+                loop(6)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                loop(30)
+                ms = (time.perf_counter() - t0) / 30 * 1e3
+                print(json.dumps(dict(masks=str(mode), depth=depth, streams=ns, ms=round(ms, 4),
+                                      frames_per_s=round(F / ms * 1e3, 1))), flush=True)
+                for s in ss:
+                    s.close()
+
 
 if __name__ == '__main__':
     main()
