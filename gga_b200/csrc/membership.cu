@@ -822,7 +822,7 @@ int launch_by_width(const SweepParams& p, int nt, dim3 grid, size_t smem, cudaSt
       case 2: return launch_sweep<MODE, 2, 1024, VEC4>(p, grid, smem, st);
       case 4: return launch_sweep<MODE, 4, 1024, VEC4>(p, grid, smem, st);
       case 8: return launch_sweep<MODE, 8, 1024, VEC4>(p, grid, smem, st);
-      default: break;
+      default: return launch_sweep<MODE, 0, 1024, VEC4>(p, grid, smem, st);
     }
   }
 #ifdef GGA_PROFILING
@@ -861,11 +861,14 @@ int run_pib(int mode, const float* points, int pts_stride, const float* boxes, v
   sp.nchunks = (num_boxes + kChunkBoxes - 1) / kChunkBoxes;
   sp.trace = nullptr;
   sp.variant = 0;
-  // 1024-thread CTAs (one per SM, 32 warps) for rows up to 8 words; 512 threads for wider rows,
-  // whose per-warp stage and tables would not fit next to 32 warps
-  int nt = sp.W <= 8 ? 1024 : 512;
+  // 1024-thread CTAs (one per SM, 32 warps) for rows up to 8 words, and for bit rows of 16 / 24 words
+  // (257..768 boxes: the sweep is bound by dependent latency per batch, twice the warps hide more of
+  // it — measured 70 -> 56 us at 8 x 50k x 512); 512 threads for 32-word rows and the int32 layouts,
+  // whose per-warp stage leaves too little room for the point ring next to 32 warps (slower there)
+  int nt = sp.W <= 8 || (mode == kModeBits && sp.W <= 24) ? 1024 : 512;
 #ifdef GGA_PROFILING
   if (g_prof.nt == 512 && sp.W >= 8) nt = 512;
+  if (g_prof.nt == 1024) nt = 1024;
   sp.trace = g_prof.trace;
   sp.variant = g_prof.variant;
 #endif
