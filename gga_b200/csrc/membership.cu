@@ -8,23 +8,25 @@
 // Design.  The brute-force test is FP32-issue bound (14 instr x N x T); the useful
 // traffic is 16 B in and 4*W B out per point.  ONE persistent kernel, no global scratch:
 //
-//  * a CTA serves one contiguous range of one frame's points.  It first builds that frame's box
-//    index in its own shared memory (~1 us, while its first point batches are already in flight):
+//  * a CTA serves the 256-point tiles r, r + rf, ... of ONE frame.  It first builds that frame's box
+//    index in its own shared memory (while its first point tile is already in flight):
 //      - the exact per-box contract terms (cos/sin of -rz through include/gga_detmath.h),
-//      - the conservative BEV rectangle of every box (box_rect),
-//      - two AXIS MASK tables: for each of kBins bins along x (and along y) a row of W words whose
-//        bit t says "the rectangle of box t overlaps this bin".  They are built without a
-//        (bin x box) loop: every box marks its first and last bin in a start / end table (4 shared
-//        atomics per box) and one warp-level XOR prefix scan per (axis, word) turns the marks into
-//        the rows.
-//  * per point: one coalesced 16-byte load, two bin numbers, maskx[bx] & masky[by] = the
-//    candidate boxes AS A BIT ROW in the output layout; the exact test runs only for the set
-//    bits and clears the ones that fail.  Sparse scenes write the row almost as loaded.
-//  * rows are staged per warp in shared memory (16-byte chunks XOR-swizzled, conflict free) so that
-//    every warp store is a full 512-byte STG.128.
+//      - the conservative BEV rectangle of every box (box_rect) and, from their extent, ONE clamped
+//        monotone bin function shared by rectangles and points (bin_of),
+//      - at most 256 boxes: a CELL TABLE (cells of 2 x 2 bins, up to 7 one-byte box ids + count per
+//        cell) filled with shared-memory atomics by all threads of the CTA,
+//      - more boxes, or a scene so dense that a cell overflows: two AXIS MASK tables — for each bin
+//        along x (and along y) a row of W words whose bit t says "the rectangle of box t overlaps this
+//        bin"; maskx[bx] & masky[by] = the candidate boxes AS A BIT ROW in the output layout.
+//  * points enter through a ring of TMA bulk copies (full / empty mbarrier per slot); per point: two
+//    bin numbers, one cell entry (or two mask rows), the exact test only for the candidates.
+//  * rows are staged per warp in shared memory as the linear image of the output (chunk order rotated
+//    per lane: conflict free) and leave as ONE bulk copy per 32-point batch.
 //  * more than 1024 boxes: the box list is served in chunks of 1024 (32 row words) per sweep.
+//  * launched with programmatic dependent launch: table reset and barrier set-up run before
+//    griddepcontrol.wait, i.e. under the previous kernel's tail.
 //
-// Culling never changes the result; every candidate is decided by inside_box() below.
+// Culling never changes the result; every candidate is decided by outside_z() / inside_xy() below.
 #include <float.h>
 
 #include "../../include/gga_detmath.h"
