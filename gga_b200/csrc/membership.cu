@@ -45,6 +45,7 @@ constexpr int kMaxSlots = 56;      // ring slots (tiles) a CTA can hold
 // (4 threads per box at 256 boxes, four cells in flight per thread).
 constexpr int kCellsSide = kBins / 2;
 constexpr int kCellIds = 7;
+constexpr int kZBins = 32;       // bins along z of the general path's third mask (30 inner, 2 border)
 constexpr int kWideCells = 256;  // a box covering more cells is kept in a short list tested for every point
 constexpr int kMaxWide = 8;
 __host__ __device__ __forceinline__ int cell_of_bin(int b) { return b >> 1; }
@@ -114,6 +115,22 @@ __device__ __forceinline__ int box_rect(float cx, float cy, float cosa, float si
   return 1;
 }
 
+// Conservative z slab of a box for the z mask of the general path.  The contract's test is
+// |fl(pz - cz)| <= RD(dz/2) with cz = fl(z + dz/2 in double); zc below is within 2 ulp of that cz and
+// the slack covers it and the rounding of the subtraction.  kind: 0 = no finite point can pass (the
+// last z bin, where NaN z lands, lists every box anyway), 1 = finite slab, 2 = every z bin.
+__device__ __forceinline__ int box_zslab(float z, float dz, float& lo, float& hi) {
+  const float h = 0.5f * dz, zc = z + h;
+  if (!(h == h) || !isfinite(zc)) return 2;   // NaN size or non-finite centre: cannot be ordered
+  if (h < 0.f) return 0;
+  if (!isfinite(h)) return 2;
+  const float slack = __fadd_ru(__fmul_ru(__fadd_ru(fabsf(zc), h), 9.5367431640625e-7f), 1e-37f);
+  lo = __fsub_rd(__fsub_rd(zc, h), slack);
+  hi = __fadd_ru(__fadd_ru(zc, h), slack);
+  if (!isfinite(lo) || !isfinite(hi)) return 2;
+  return 1;
+}
+
 __device__ __forceinline__ uint32_t f2ord(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -145,6 +162,9 @@ __host__ __device__ __forceinline__ int mask_stride(int wc) { return wc >= 8 ? w
 // everything outside the boxes' extent; NaN maps to the last bin (fminf returns the non-NaN operand).
 __device__ __forceinline__ int bin_of(float v, float inv, float off) {
   return (int)fmaxf(fminf(__fmaf_rn(v, inv, off), (float)(kBins - 1)), 0.f);
+}
+__device__ __forceinline__ int zbin_of(float v, float inv, float off) {  // same construction, kZBins bins
+  return (int)fmaxf(fminf(__fmaf_rn(v, inv, off), (float)(kZBins - 1)), 0.f);
 }
 
 // ---- bulk asynchronous copies (TMA, 1-D) and their mbarriers -------------------------------------
@@ -200,9 +220,13 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
   constexpr bool kCells = WC != 0;                    // <= 256 boxes: candidates come from the cell table
   constexpr int kStages = kBulk && WC != 0 ? 2 : 1;   // stage buffers per warp (narrow rows: double buffered)
   constexpr int R = kWarps / kTileBatches;            // point tiles consumed at a time (8 warps per tile)
+  // general path, 1024-thread CTAs (bit rows of 16 / 24 words): a third mask along z.  Dense indoor
+  // scenes lose ~half of their candidates to it (c3 56 -> 48 us); with 32-word rows the extra 128-byte
+  // gather per point costs more than the candidates it removes (c5 87 -> 113 us), so not there.
+  constexpr bool kZ = WC == 0 && NT == 1024;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint32_t s_wext[kWarps][4];  // per-warp extent of the finite box rectangles
-  __shared__ float s_bin[4];              // bin function of the sweep: invx, offx, invy, offy
+  __shared__ uint32_t s_wext[kWarps][6];  // per-warp extent of the finite box rectangles (and z slabs)
+  __shared__ float s_bin[6];              // bin function of the sweep: invx, offx, invy, offy, invz, offz
   __shared__ int s_flags[2];              // [0] some cell holds more than kCellIds boxes (axis masks needed), [1] cells unusable
   __shared__ int s_nwide;
   __shared__ int s_wide[kMaxWide];
@@ -237,16 +261,18 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
   float4* terms = reinterpret_cast<float4*>(smem_raw);           // [2 tcap]
   uint32_t* mx = reinterpret_cast<uint32_t*>(terms + 2 * tcap);  // [kBins][mask_stride(wc)]
   uint32_t* my = mx + kBins * mcap;
+  uint32_t* mz = my + kBins * mcap;                              // [kZBins][mask_stride(wc)] (general path only)
+  constexpr int kMaskRows = 2 * kBins + (kZ ? kZBins : 0);
   // per-warp stage: the linear image of the 32 rows of a batch; two buffers when the rows leave
   // through the bulk copy engine (one is being read by it while the next batch is built)
-  uint32_t* stage_all = my + kBins * mcap;
+  uint32_t* stage_all = mx + kMaskRows * mcap;
   uint32_t* stage_base = stage_all + warp * (kStages * 32 * wcap);
   uint32_t* cells = stage_all + kWarps * (kStages * 32 * wcap);  // [kCellsSide^2][2] (sparse path only)
   unsigned char* ring = reinterpret_cast<unsigned char*>(cells + (kCells ? kCellsSide * kCellsSide * 2 : 0));
   const uint32_t tile_bytes = 1024u * (uint32_t)p.pts_stride;  // 256 points
   const int S = p.ring_slots / R;                              // ring slots of this warp group
   auto reset_tables = [&](bool again) {
-    for (int i = tid; i < (2 * kBins * mcap) >> 2; i += NT) reinterpret_cast<uint4*>(mx)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (kMaskRows * mcap) >> 2; i += NT) reinterpret_cast<uint4*>(mx)[i] = make_uint4(0u, 0u, 0u, 0u);
     if constexpr (kCells) {
       for (int i = tid; i < (kCellsSide * kCellsSide * 2) >> 2; i += NT) reinterpret_cast<uint4*>(cells)[i] = make_uint4(0u, 0u, 0u, 0u);
       if (tid == 0) { s_flags[0] = 0; s_flags[1] = 0; s_nwide = 0; }
@@ -335,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
         }
       }
       stamp();
-      float invx = 0.f, invy = 0.f, offx = 1.f, offy = 1.f;
+      float invx = 0.f, invy = 0.f, offx = 1.f, offy = 1.f, invz = 0.f, offz = 1.f;
       auto exact_terms = [&]() {
         const int e = eoff != 0 ? tid - eoff : tid;
 #pragma unroll
@@ -349,10 +375,12 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
         }
       };
       int bx0[KB], bx1[KB], by0[KB], by1[KB], kind[KB];
+      int bz0[KB], bz1[KB];  // z bins of the box's slab (general path)
       if (box_warp) {
         // the box warps: rectangles and extent; they synchronise among themselves on named barrier 1
-        float rx0[KB], rx1[KB], ry0[KB], ry1[KB];
-        uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mxx = 0u, mxy = 0u;
+        float rx0[KB], rx1[KB], ry0[KB], ry1[KB], rz0[KB], rz1[KB];
+        int zkind[KB];
+        uint32_t mnx = 0xffffffffu, mny = 0xffffffffu, mxx = 0u, mxy = 0u, mnz = 0xffffffffu, mxz = 0u;
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
           const int t = tid + k * NT;
@@ -371,11 +399,23 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
               mnx = min(mnx, f2ord(rx0[k])); mxx = max(mxx, f2ord(rx1[k]));
               mny = min(mny, f2ord(ry0[k])); mxy = max(mxy, f2ord(ry1[k]));
             }
+            if constexpr (kZ) {
+              rz0[k] = rz1[k] = 0.f;
+              zkind[k] = kind[k] == 0 ? 0 : box_zslab(bq[k][2], bq[k][5], rz0[k], rz1[k]);
+              if (zkind[k] == 1) { mnz = min(mnz, f2ord(rz0[k])); mxz = max(mxz, f2ord(rz1[k])); }
+            }
+          } else if constexpr (kZ) {
+            zkind[k] = 0;
+            rz0[k] = rz1[k] = 0.f;
           }
         }
+        if constexpr (kZ) { mnz = __reduce_min_sync(0xffffffffu, mnz); mxz = __reduce_max_sync(0xffffffffu, mxz); }
         mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
         mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
-        if (lane == 0) { s_wext[warp][0] = mnx; s_wext[warp][1] = mny; s_wext[warp][2] = mxx; s_wext[warp][3] = mxy; }
+        if (lane == 0) {
+          s_wext[warp][0] = mnx; s_wext[warp][1] = mny; s_wext[warp][2] = mxx; s_wext[warp][3] = mxy;
+          if constexpr (kZ) { s_wext[warp][4] = mnz; s_wext[warp][5] = mxz; }
+        }
         asm volatile("bar.sync 1, %0;" ::"r"(32 * nbw) : "memory");  // warp extents published
         request_rest();
         stamp();
@@ -397,9 +437,29 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
           if (!isfinite(offx)) { invx = 0.f; offx = 1.f; }
           if (!isfinite(offy)) { invy = 0.f; offy = 1.f; }
         }
-        if (tid == 0) { s_bin[0] = invx; s_bin[1] = offx; s_bin[2] = invy; s_bin[3] = offy; }
+        if constexpr (kZ) {  // the same for the z slabs: kZBins - 2 inner bins tile their extent
+          uint32_t z0 = 0xffffffffu, z1 = 0u;
+          if (lane < nbw) { z0 = s_wext[lane][4]; z1 = s_wext[lane][5]; }
+          z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
+          if (z0 != 0xffffffffu) {
+            const float gz0 = ord2f(z0), wz = ord2f(z1) - gz0;
+            if (wz > 0.f && isfinite(wz)) invz = __fdividef((float)(kZBins - 2), wz);
+            if (!isfinite(invz) || !(invz >= 0.f)) invz = 0.f;
+            offz = __fsub_rn(1.f, __fmul_rn(gz0, invz));
+            if (!isfinite(offz)) { invz = 0.f; offz = 1.f; }
+          }
+        }
+        if (tid == 0) {
+          s_bin[0] = invx; s_bin[1] = offx; s_bin[2] = invy; s_bin[3] = offy;
+          if constexpr (kZ) { s_bin[4] = invz; s_bin[5] = offz; }
+        }
 #pragma unroll
         for (int k = 0; k < KB; ++k) {
+          if constexpr (kZ) {
+            bz0[k] = 0; bz1[k] = kZBins - 1;                      // zkind 2: every z bin
+            if (zkind[k] == 1) { bz0[k] = zbin_of(rz0[k], invz, offz); bz1[k] = zbin_of(rz1[k], invz, offz); }
+            if (zkind[k] == 0) { bz0[k] = 1; bz1[k] = 0; }        // none (but the last bin, below)
+          }
           bx0[k] = 0; bx1[k] = kBins - 1; by0[k] = 0; by1[k] = kBins - 1;
           if (kind[k] == 1) {
             bx0[k] = bin_of(rx0[k], invx, offx); bx1[k] = bin_of(rx1[k], invx, offx);
@@ -478,6 +538,13 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
             uint32_t* cy_ = my + (t >> 5);
             for (int b = bx0[k]; b <= bx1[k]; ++b) atomicOr(cx_ + b * ms, bit);
             for (int b = by0[k]; b <= by1[k]; ++b) atomicOr(cy_ + b * ms, bit);
+            if constexpr (kZ) {
+              uint32_t* cz_ = mz + (t >> 5);
+              for (int b = bz0[k]; b <= bz1[k]; ++b) atomicOr(cz_ + b * ms, bit);
+              // the last bin takes every point above the slabs and every NaN z — and a NaN z passes
+              // the z test of EVERY box (the CPU op's `fabsf(z - cz) > dz/2` is false for NaN)
+              if (bz1[k] != kZBins - 1) atomicOr(cz_ + (kZBins - 1) * ms, bit);
+            }
           }
         }
         stamp();
@@ -485,6 +552,7 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
       }
       if (!kCells || need_masks || eoff == 0) __syncthreads();  // (all three conditions are CTA-uniform)
       invx = s_bin[0]; offx = s_bin[1]; invy = s_bin[2]; offy = s_bin[3];
+      if constexpr (kZ) { invz = s_bin[4]; offz = s_bin[5]; }
 #ifdef GGA_PROFILING
       if ((p.variant & 512) && tj == 0 && lane == 0)
         for (int k = 1; k < S; ++k) request_tile(k, tr + R * k);
@@ -568,6 +636,7 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
           uint32_t nz = 0u;
           const uint4* ax = reinterpret_cast<const uint4*>(mx + bx * ms);
           const uint4* ay = reinterpret_cast<const uint4*>(my + by * ms);
+          const uint4* az = reinterpret_cast<const uint4*>(mz + (kZ ? zbin_of(pt.z, invz, offz) : 0) * ms);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j >= nck) break;
@@ -576,6 +645,10 @@ __global__ void __launch_bounds__(NT, 1) pib_sweep_kernel(const SweepParams p) {
             uint4 a = ax[k];
             const uint4 b = ay[k];
             a.x &= b.x; a.y &= b.y; a.z &= b.z; a.w &= b.w;
+            if constexpr (kZ) {
+              const uint4 c = az[k];
+              a.x &= c.x; a.y &= c.y; a.z &= c.z; a.w &= c.w;
+            }
             reinterpret_cast<uint4*>(row)[k] = a;
             nz |= ((a.x != 0u ? 1u : 0u) | (a.y != 0u ? 2u : 0u) | (a.z != 0u ? 4u : 0u) | (a.w != 0u ? 8u : 0u)) << (4 * k);
           }
@@ -792,7 +865,8 @@ size_t sweep_fixed_smem(int mode, int T, int W, int nt) {
   const size_t wcap = W < 32 ? W : 32;
   const size_t stages = (mode == kModeBits && W >= 4 && W <= 8) ? 2 : 1;  // double-buffered narrow rows (bulk store)
   const size_t cells = W <= 8 ? (size_t)kCellsSide * kCellsSide * 8 : 0;  // sparse path (<= 256 boxes)
-  return tcap * 32 + (size_t)2 * kBins * mask_stride((int)wcap) * 4 + (size_t)(nt / 32) * stages * 32 * wcap * 4 + cells;
+  const size_t mask_rows = 2 * kBins + (W > 8 && nt == 1024 ? kZBins : 0);  // general path at 1024 threads: z mask too
+  return tcap * 32 + mask_rows * mask_stride((int)wcap) * 4 + (size_t)(nt / 32) * stages * 32 * wcap * 4 + cells;
 }
 
 template <int MODE, int WC, int NT, bool VEC4>

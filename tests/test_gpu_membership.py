@@ -133,9 +133,11 @@ def test_random_shapes_bit_exact(M, T):
         assert ref.sum() > 0
 
 
-def test_adversarial_boxes_and_points():
+@pytest.mark.parametrize('T', [40, 300, 700, 1100])
+def test_adversarial_boxes_and_points(T):
+    """T = 40: cell-table path; 300 / 700: axis masks (x, y and z) with 16- / 24-word rows; 1100: two sweeps."""
     rng = np.random.default_rng(99)
-    boxes = synth.make_boxes(rng, 40)
+    boxes = synth.make_boxes(rng, T)
     boxes[4] = [10, 0, -1, 0, 2, 2, 0.3]            # zero width: contains nothing
     boxes[5] = [10, 0, -1, -2, 2, 2, 0.3]           # negative size
     boxes[6] = [np.nan, 0, -1, 2, 2, 2, 0.3]        # NaN centre
@@ -150,13 +152,29 @@ def test_adversarial_boxes_and_points():
     boxes[15] = [3e38, 3e38, 0, 3e38, 3e38, 1, 0.5]
     boxes[16] = [20, 5, -1.5, 3, 1.5, 1.5, 1e4]     # huge yaw (Payne-Hanek path)
     boxes[17] = [20, 5, -1.5, 3, 1.5, 1.5, -3e38]
+    # z slabs: far above / below the others, stacked at one place, a subnormal height, non-finite z
+    boxes[18] = [30, 10, 40, 4, 4, 2, 0.2]
+    boxes[19] = [30, 10, -60, 4, 4, 2, 0.2]
+    boxes[20] = [30, 10, 0, 4, 4, 1, 0.2]
+    boxes[21] = [30, 10, 1, 4, 4, 1, 0.2]           # its bottom face is box 20's top face (both closed)
+    boxes[22] = [30, 10, 2, 4, 4, 1e-42, 0.2]       # subnormal height: only z == 2 exactly
+    boxes[23] = [30, 10, np.inf, 4, 4, 1, 0.2]
+    boxes[24] = [30, 10, -np.inf, 4, 4, np.inf, 0.2]
+    boxes[25] = [30, 10, 1e30, 4, 4, 1e30, 0.2]
+    boxes[26] = [30, 10, np.nan, 4, 4, 1, 0.2]      # NaN z: the z test passes for every point
     pts = synth.make_points(rng, 20000, boxes)
+    pts[20:34, :3] = [[30, 10, 40], [30, 10, 42], [30, 10, 42.00001], [30, 10, -60], [30, 10, -58], [30, 10, 1],
+                      [30, 10, 0], [30, 10, 2], [30, 10, np.nan], [30, 10, 1e30], [30, 10, 2e30], [30, 10, 3e38],
+                      [30, 10, -3e38], [30, 10, np.float32(2) + np.float32(2.4e-7)]]
     pts[:6, :3] = [[np.nan, 0, 0], [0, np.nan, 0], [10, 0, np.nan], [np.inf, 0, 0], [0, -np.inf, 0],
                    [10, 0, np.inf]]
     pts[6:12, :3] = [[10, 0, -1], [10, 0, 1], [11, 0, 0], [9, 0, 0], [1e30, 0, -0.5], [20, 5, -1]]
     ref = check_against_oracle(pts, boxes)
     assert ref[:, 10].sum() > 10000 and ref[:, 4].sum() == 0 and ref[:, 6].sum() == 0
     assert ref[2, 12] == 1  # NaN z inside the NaN-height box at its centre (contract quirk)
+    assert ref[20, 18] and ref[21, 18] and not ref[22, 18] and ref[23, 19] and ref[24, 19]   # closed z faces
+    assert ref[25, 20] and ref[25, 21] and ref[27, 21] and ref[27, 22] and ref[28, 20]        # shared face, NaN z
+    assert ref[20:34, 26].all() and ref[30, 25]
 
 
 def test_only_degenerate_boxes_and_empty_inputs():
