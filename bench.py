@@ -477,8 +477,9 @@ def run_steps_workload(args, x, cfg):
     def plan(K):
         """graphs that together run exactly K steps: K // chunk replays of a chunk graph + one remainder graph"""
         chunk = min(K, GRAPH_CHUNK)
-        chunk -= chunk % n_sets if chunk > n_sets else 0   # whole rotations keep the sets evenly used
-        chunk = max(chunk, 1)
+        if K > GRAPH_CHUNK:      # several replays: whole rotations keep the sets evenly used
+            chunk -= chunk % n_sets
+        chunk = max(chunk, 1)    # (K <= GRAPH_CHUNK: ONE graph holds all K steps — one launch in the timed region)
         full, rem = divmod(K, chunk)
         g_chunk = capture_steps(chunk)
         g_rem = capture_steps(rem, first=(full * chunk) % n_sets) if rem else None
