@@ -363,16 +363,18 @@ def setup_dist():
     return x
 
 
-def ramp_reps(x, fn, seconds=0.25):
+def ramp_reps(x, fn, seconds=0.25, sync=None):
     """How often to repeat fn() so that ~`seconds` of this work run before the timed region (SM clock
     ramp).  fn may hold collectives, so every rank must repeat it the SAME number of times: the count
     is derived from one probe run and agreed on through a max over ranks."""
     import math
-    import torch
-    torch.cuda.synchronize()
+    if sync is None:
+        import torch
+        sync = torch.cuda.synchronize
+    sync()
     t0 = time.perf_counter()
     fn()
-    torch.cuda.synchronize()
+    sync()
     t1 = x.max_over_ranks(time.perf_counter() - t0)
     return int(min(5000, max(1, math.ceil(seconds / max(t1, 1e-6)))))
 

@@ -31,6 +31,24 @@ def _worker(rank, world, port, q):
         local = torch.arange(lo, hi, dtype=torch.int32).reshape(-1, 1).repeat(1, 4)
         allr = gd.gather_frames(local, n)
         assert allr.shape == (n, 4) and torch.equal(allr[:, 0], torch.arange(n, dtype=torch.int32))
+        # bench.py's warm-up repetition count must be the SAME on every rank although the ranks time
+        # their probe run differently (the repeated function holds collectives: a rank that looped once
+        # more than another deadlocked the 8-GPU run)
+        import sys
+        import time
+        import types
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+
+        def max_over_ranks(v):
+            t = torch.tensor([v], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        x = types.SimpleNamespace(max_over_ranks=max_over_ranks)
+        reps = bench.ramp_reps(x, lambda: time.sleep(0.002 * (1 + 4 * rank)), seconds=0.05, sync=lambda: None)
+        both = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(both, torch.tensor([reps], dtype=torch.int64))
+        assert int(both[0]) == int(both[1]) and 3 <= reps <= 6, (reps, both)
         q.put((rank, 'ok'))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
